@@ -1,0 +1,184 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the build container (where /root/reference exists):  python -m oracle.make_golden
+The reference has no golden vectors of its own, so these files ARE the pin: seeded
+synthetic scenes of SURVEY.md §8d pushed through volsdf/model/network.py::VolSDFNetwork.forward and
+network_bg.py::VolSDFNetworkBG.forward, with torch.searchsorted / torch.sort wrapped (not modified) to
+record the sampler's per-iteration indices.  Weights are not stored: they are re-created on the test
+side from torch.manual_seed(0) + scene.perturb_, and a checksum in each file guards that.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+import svolsdf_b200.conf as C  # noqa: E402
+import svolsdf_b200.scene as S  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+class Capture(object):
+    """Wraps torch.searchsorted / torch.sort while the reference runs and records their index outputs."""
+
+    def __init__(self):
+        self.inds, self.sort_idx = [], []
+
+    def __enter__(self):
+        self._ss, self._sort = torch.searchsorted, torch.sort
+
+        def ss(*a, **k):
+            r = self._ss(*a, **k)
+            self.inds.append(r.clone())
+            return r
+
+        def srt(*a, **k):
+            r = self._sort(*a, **k)
+            self.sort_idx.append(r[1].clone())
+            return r
+
+        torch.searchsorted, torch.sort = ss, srt
+        return self
+
+    def __exit__(self, *exc):
+        torch.searchsorted, torch.sort = self._ss, self._sort
+
+
+def param_checksum(model):
+    return float(sum(p.detach().double().sum() for p in model.parameters())), \
+        float(sum(p.detach().double().abs().sum() for p in model.parameters()))
+
+
+def grad_fingerprint(model, n_pick=32, seed=11):
+    """Per-parameter (L2 norm, sum, n_pick sampled entries at seeded positions)."""
+    g = torch.Generator().manual_seed(seed)
+    fp = {}
+    for name, p in sorted(model.named_parameters(), key=lambda kv: kv[0]):
+        gr = p.grad.detach().reshape(-1).double() if p.grad is not None else torch.zeros(p.numel(), dtype=torch.double)
+        pick = torch.randint(0, gr.numel(), (n_pick,), generator=g)
+        fp['grad_norm/' + name] = np.array(float(gr.norm()))
+        fp['grad_sum/' + name] = np.array(float(gr.sum()))
+        fp['grad_pick_idx/' + name] = pick.numpy()
+        fp['grad_pick/' + name] = gr[pick].numpy()
+    return fp
+
+
+def build(ns, kind, perturb, beta):
+    torch.manual_seed(0)
+    if kind == 'dtu':
+        model = ns.network.VolSDFNetwork(C.dtu_model_conf())
+    else:
+        model = ns.network_bg.VolSDFNetworkBG(C.bmvs_model_conf())
+    if perturb or beta is not None:
+        S.perturb_(model, seed=7, w_std=0.02 if perturb else 0.0, b_std=0.01 if perturb else 0.0, beta=beta)
+    return model
+
+
+def run_case(ns, name, kind, n_rays, training, perturb=False, beta=None, fast=None):
+    model = build(ns, kind, perturb, beta)
+    inp = S.make_input(kind, n_rays)
+    rec = {'meta/kind': kind, 'meta/n_rays': n_rays, 'meta/training': training, 'meta/perturb': perturb,
+           'meta/beta': -1.0 if beta is None else beta}
+    cs = param_checksum(model)
+    rec['meta/param_sum'], rec['meta/param_abs_sum'] = cs
+    torch.manual_seed(123)
+    with Capture() as cap:
+        if training:
+            model.train()
+            out = model(inp, fast=1)
+        else:
+            model.eval()
+            out = model(inp) if fast is None else model(inp, fast=fast)
+    for k, v in out.items():
+        rec['out/' + k] = v.detach().numpy()
+    for i, t in enumerate(cap.inds):
+        rec['sampler/inds_%d' % i] = t.numpy().astype(np.int32)
+    for i, t in enumerate(cap.sort_idx):
+        rec['sampler/sort_idx_%d' % i] = t.numpy().astype(np.int32)
+    rec['sampler/n_searchsorted'] = len(cap.inds)
+    if training:
+        gt = S.gt_rgb(n_rays)
+        rgb_loss = (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean()
+        eik = ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+        loss = rgb_loss + 0.1 * eik
+        if ns.loss is not None:  # cross-check against the reference's own VolSDFLoss
+            lf = ns.loss.VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1)
+            lf.iter_step = 0
+            ref_loss = lf(out, {'rgb': gt})['loss']
+            assert abs(float(ref_loss) - float(loss)) < 1e-7, (float(ref_loss), float(loss))
+        model.zero_grad()
+        loss.backward()
+        rec['loss'] = np.array(float(loss))
+        rec.update(grad_fingerprint(model))
+    path = os.path.join(OUT, name + '.npz')
+    np.savez_compressed(path, **rec)
+    print('%-28s %8.1f KB  iters=%d' % (name, os.path.getsize(path) / 1024.0, len(cap.inds)))
+    return rec
+
+
+def unit_vectors(ns):
+    """Sub-module level vectors: PE, SDF MLP forward / gradient, rendering MLP, density, camera, bg lift."""
+    rec = {}
+    model = build(ns, 'dtu', True, None)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(256, 3, generator=g) * 2 - 1) * 2.4   # some points beyond |x|=3 -> sphere branch
+    rec['x'] = x.numpy()
+    rec['pe6'] = ns.embedder.get_embedder(6)[0](x).numpy()
+    imp = model.implicit_network
+    with torch.no_grad():
+        rec['sdf_forward'] = imp(x.clone()).numpy()
+        rec['sdf_vals'] = imp.get_sdf_vals(x.clone()).numpy()
+    sdf, feat, grad = imp.get_outputs(x.clone())
+    rec['out_sdf'], rec['out_feat'], rec['out_grad'] = sdf.detach().numpy(), feat.detach().numpy(), grad.detach().numpy()
+    rec['gradient'] = imp.gradient(x.clone()).detach().numpy()
+    d = torch.nn.functional.normalize(torch.randn(256, 3, generator=g), dim=1)
+    rec['view_dirs'] = d.numpy()
+    rec['rgb'] = model.rendering_network(x, grad.detach(), d, feat.detach()).detach().numpy()
+    s = torch.randn(64, 98, generator=g) * 0.3
+    rec['dens_sdf'] = s.numpy()
+    rec['dens'] = model.density(s).detach().numpy()
+    z = torch.sort(torch.rand(64, 98, generator=g) * 6, -1)[0]
+    rec['vr_z'] = z.numpy()
+    w, _ = model.volume_rendering(z, s.reshape(-1, 1))
+    rec['vr_weights'] = w.detach().numpy()
+    inp = S.make_input('dtu', 128)
+    rd, cl = ns.rend_util.get_camera_params(inp['uv'], inp['pose'], inp['intrinsics'])
+    rec['cam_uv'], rec['cam_dirs'], rec['cam_loc'] = inp['uv'].numpy(), rd.numpy(), cl.numpy()
+    rec['sphere_isect'] = ns.rend_util.get_sphere_intersections(cl.repeat(128, 1), rd[0], r=3.0).numpy()
+    bgm = build(ns, 'bmvs', True, None)
+    depth = torch.rand(128, 32, generator=g)
+    o = cl.unsqueeze(1).repeat(128, 32, 1)
+    dd = rd[0].unsqueeze(1).repeat(1, 32, 1)
+    pts, dreal = bgm.depth2pts_outside(o, dd, depth)
+    rec['bg_depth'], rec['bg_pts'], rec['bg_depth_real'] = depth.numpy(), pts.numpy(), dreal.numpy()
+    with torch.no_grad():
+        bo = bgm.bg_implicit_network(pts.reshape(-1, 4)[:256])
+        rec['bg_sdf_forward'] = bo.numpy()
+        rec['bg_rgb'] = bgm.bg_rendering_network(None, None, dd.reshape(-1, 3)[:256], bo[:, 1:]).numpy()
+    rec['meta/param_sum_dtu'], _ = param_checksum(model)
+    rec['meta/param_sum_bmvs'], _ = param_checksum(bgm)
+    path = os.path.join(OUT, 'units.npz')
+    np.savez_compressed(path, **rec)
+    print('%-28s %8.1f KB' % ('units', os.path.getsize(path) / 1024.0))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_import.load()
+    torch.set_num_threads(8)
+    unit_vectors(ns)
+    run_case(ns, 'dtu_eval_r64', 'dtu', 64, False)
+    run_case(ns, 'dtu_eval_r32_beta001', 'dtu', 32, False, perturb=True, beta=0.01)
+    run_case(ns, 'dtu_train_r64', 'dtu', 64, True)
+    run_case(ns, 'dtu_train_r64_pert', 'dtu', 64, True, perturb=True, beta=0.02)
+    run_case(ns, 'bmvs_eval_r32', 'bmvs', 32, False, perturb=True)
+    run_case(ns, 'bmvs_train_r32', 'bmvs', 32, True, perturb=True)
+
+
+if __name__ == '__main__':
+    main()

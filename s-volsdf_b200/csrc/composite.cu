@@ -1,0 +1,356 @@
+// K11: Laplace/Abs density + transmittance + alpha compositing, fused forward and fused backward.
+// One warp per ray; the ray's rows (z, sdf, rgb[, normals]) are staged in shared memory with coalesced
+// loads, then every lane owns a contiguous chunk of C samples so the exclusive prefix sum is one local
+// scan + one 5-step warp scan.  HBM-bound: algorithmic bytes per ray in DESIGN.md §compositor.
+//
+// Reference: density.py:21-35, network.py:281-295 (volume_rendering), :239-248 (rgb/depth),
+// :270-276 (normal map), network_bg.py:147-180 (fg tail + bg pass).  Math of the backward: SURVEY.md App. G.
+#include "svs_common.cuh"
+
+namespace svs {
+
+constexpr int kCompWarps = 4;
+
+template <int C>
+struct CompSmem {
+  float z[kCompWarps][32 * C + 1];
+  float s[kCompWarps][32 * C];
+  float w[kCompWarps][32 * C];
+  float c[kCompWarps][32 * C * 3];
+};
+
+__device__ __forceinline__ float beta_of(const float* beta_param, float beta_min) {
+  return fabsf(__ldg(beta_param)) + beta_min;  // density.py:28-30
+}
+
+// sigma and the autograd-form derivative d sigma / d s
+__device__ __forceinline__ float density_fwd(float s, float beta, bool abs_density, float* em_out) {
+  if (abs_density) {
+    *em_out = 0.f;
+    return fabsf(s);
+  }
+  float em = expm1f(-fabsf(s) / beta);
+  *em_out = em;
+  float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  return (1.0f / beta) * (0.5f + 0.5f * sg * em);
+}
+
+// exclusive prefix sum over the warp's 32*C elements held as v[C] per lane (lane-contiguous layout);
+// returns the grand total.  Accumulates in fp64 like torch's CPU cumsum.
+template <int C>
+__device__ __forceinline__ double warp_excl_scan(const float (&v)[C], double (&excl)[C], int lane) {
+  double run = 0.0;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    excl[j] = run;
+    run += (double)v[j];
+  }
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double base = incl - run;
+#pragma unroll
+  for (int j = 0; j < C; ++j) excl[j] += base;
+  return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                     const float* __restrict__ normals, const float* __restrict__ beta_param, float beta_min,
+                     const float* __restrict__ depth_scale, const float* __restrict__ z_max, int64_t R, int S,
+                     int flags, float* __restrict__ weights, float* __restrict__ rgb_values,
+                     float* __restrict__ depth_values, float* __restrict__ normal_map,
+                     float* __restrict__ bg_trans) {
+  __shared__ CompSmem<C> sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
+             tail = flags & SVS_COMP_ZMAX_TAIL;
+  const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
+  for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
+    const float* zr = z + ray * S;
+    const float* sr = sdf + ray * S;
+    for (int i = lane; i < 32 * C; i += 32) {
+      sm.z[warp][i] = (i < S) ? zr[i] : 0.f;
+      sm.s[warp][i] = (i < S) ? sr[i] : 0.f;
+    }
+    if (rgb) {
+      const float* cr = rgb + ray * S * 3;
+      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = cr[i];
+    }
+    if (lane == 0) sm.z[warp][32 * C] = 0.f;
+    __syncwarp();
+    float E[C], zz[C];
+    double excl[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      float zi = sm.z[warp][i];
+      zz[j] = zi;
+      float em;
+      float sigma = density_fwd(sm.s[warp][i], beta, abs_d, &em);
+      float d;
+      if (i < S - 1) {
+        float zn = sm.z[warp][i + 1];
+        d = rev ? (zi - zn) : (zn - zi);
+      } else if (i == S - 1) {
+        d = tail ? (__ldg(z_max + ray) - zi) : 1e10f;
+      } else {
+        d = 0.f;
+      }
+      E[j] = (i < S) ? d * sigma : 0.f;
+    }
+    double total = warp_excl_scan<C>(E, excl, lane);
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_w = 0.f, acc_wz = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      float T = expf(-(float)excl[j]);
+      float a = 1.0f - expf(-E[j]);
+      float w = (i < S) ? a * T : 0.f;
+      if (i < S) {
+        weights[ray * S + i] = w;
+        sm.w[warp][i] = w;
+        acc_w += w;
+        acc_wz += w * zz[j];
+        if (rgb) {
+          acc_r += w * sm.c[warp][3 * i];
+          acc_g += w * sm.c[warp][3 * i + 1];
+          acc_b += w * sm.c[warp][3 * i + 2];
+        }
+      }
+    }
+    acc_w = warp_sum(acc_w);
+    acc_wz = warp_sum(acc_wz);
+    if (rgb) {
+      acc_r = warp_sum(acc_r);
+      acc_g = warp_sum(acc_g);
+      acc_b = warp_sum(acc_b);
+    }
+    float nr = 0.f, ng = 0.f, nb = 0.f;
+    if (normal_map) {  // eval: sum w * g/|g|  (network.py:270-274; no eps, as the reference)
+      __syncwarp();
+      const float* gr = normals + ray * S * 3;
+      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = gr[i];
+      __syncwarp();
+      for (int i = lane; i < S; i += 32) {
+        float gx = sm.c[warp][3 * i], gy = sm.c[warp][3 * i + 1], gz = sm.c[warp][3 * i + 2];
+        float n = sqrtf(gx * gx + gy * gy + gz * gz);
+        float w = sm.w[warp][i];
+        nr += w * (gx / n);
+        ng += w * (gy / n);
+        nb += w * (gz / n);
+      }
+      nr = warp_sum(nr);
+      ng = warp_sum(ng);
+      nb = warp_sum(nb);
+    }
+    if (lane == 0) {
+      if (rgb_values) {
+        rgb_values[ray * 3] = acc_r;
+        rgb_values[ray * 3 + 1] = acc_g;
+        rgb_values[ray * 3 + 2] = acc_b;
+      }
+      if (depth_values) {
+        float ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
+        depth_values[ray] = ds * (acc_wz / (acc_w + 1e-8f));
+      }
+      if (normal_map) {
+        normal_map[ray * 3] = nr;
+        normal_map[ray * 3 + 1] = ng;
+        normal_map[ray * 3 + 2] = nb;
+      }
+      if (bg_trans) bg_trans[ray] = expf(-(float)total);
+    }
+    __syncwarp();
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                     const float* __restrict__ beta_param, float beta_min,
+                     const float* __restrict__ depth_scale, const float* __restrict__ z_max, int64_t R, int S,
+                     int flags, const float* __restrict__ d_rgb_values, const float* __restrict__ d_depth_values,
+                     const float* __restrict__ d_weights, const float* __restrict__ d_bg_trans,
+                     float* __restrict__ d_sdf, float* __restrict__ d_rgb, float* __restrict__ d_beta_param) {
+  __shared__ CompSmem<C> sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
+             tail = flags & SVS_COMP_ZMAX_TAIL;
+  const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
+  float dbeta_acc = 0.f;
+  for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
+    const float* zr = z + ray * S;
+    const float* sr = sdf + ray * S;
+    for (int i = lane; i < 32 * C; i += 32) {
+      sm.z[warp][i] = (i < S) ? zr[i] : 0.f;
+      sm.s[warp][i] = (i < S) ? sr[i] : 0.f;
+    }
+    if (rgb) {
+      const float* cr = rgb + ray * S * 3;
+      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = cr[i];
+    }
+    __syncwarp();
+    const float gr = d_rgb_values ? __ldg(d_rgb_values + ray * 3) : 0.f;
+    const float gg = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 1) : 0.f;
+    const float gb = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 2) : 0.f;
+    const float gdep = d_depth_values ? __ldg(d_depth_values + ray) : 0.f;
+    const float gbt = (tail && d_bg_trans) ? __ldg(d_bg_trans + ray) : 0.f;
+    const float ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
+    float E[C], zz[C], dl[C], sig[C], em[C], ss[C];
+    double excl[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      float zi = sm.z[warp][i];
+      zz[j] = zi;
+      ss[j] = sm.s[warp][i];
+      sig[j] = density_fwd(ss[j], beta, abs_d, &em[j]);
+      float d;
+      if (i < S - 1) {
+        float zn = sm.z[warp][i + 1];
+        d = rev ? (zi - zn) : (zn - zi);
+      } else if (i == S - 1) {
+        d = tail ? (__ldg(z_max + ray) - zi) : 1e10f;
+      } else {
+        d = 0.f;
+      }
+      dl[j] = d;
+      E[j] = (i < S) ? d * sig[j] : 0.f;
+    }
+    double total = warp_excl_scan<C>(E, excl, lane);
+    float w[C], Te[C];
+    float acc_w = 0.f, acc_wz = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      float T = expf(-(float)excl[j]);
+      float ee = expf(-E[j]);
+      w[j] = (i < S) ? (1.0f - ee) * T : 0.f;
+      Te[j] = T * ee;
+      acc_w += w[j];
+      acc_wz += w[j] * zz[j];
+    }
+    acc_w = warp_sum(acc_w);
+    acc_wz = warp_sum(acc_wz);
+    const float Wt = acc_w + 1e-8f;
+    // w_hat_i = c_i . dL/drgb + dL/dw_i + dL/ddepth * ds * (z_i*Wt - sum(wz)) / Wt^2
+    float what[C], ww[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      float v = 0.f;
+      if (i < S) {
+        if (rgb) v = sm.c[warp][3 * i] * gr + sm.c[warp][3 * i + 1] * gg + sm.c[warp][3 * i + 2] * gb;
+        if (d_weights) v += d_weights[ray * S + i];
+        v += gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
+      }
+      what[j] = v;
+      ww[j] = v * w[j];
+    }
+    // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
+    double excl2[C];
+    double tot2 = warp_excl_scan<C>(ww, excl2, lane);
+    const float bgt = tail ? expf(-(float)total) : 0.f;
+    float dbeta = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int i = lane * C + j;
+      if (i < S) {
+        float suffix = (float)(tot2 - excl2[j] - (double)ww[j]);
+        float dE = what[j] * Te[j] - suffix - gbt * bgt;
+        float dsig = dl[j] * dE;
+        float dsdf;
+        if (abs_d) {
+          float sg = (ss[j] > 0.f) ? 1.f : ((ss[j] < 0.f) ? -1.f : 0.f);
+          dsdf = dsig * sg;
+        } else {
+          float e = em[j] + 1.0f;  // autograd's expm1 backward uses result + 1
+          float nz = (ss[j] != 0.f) ? 1.f : 0.f;
+          dsdf = -dsig * nz * e / (2.0f * beta * beta);
+          dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
+        }
+        d_sdf[ray * S + i] = dsdf;
+        sm.w[warp][i] = w[j];
+      }
+    }
+    dbeta_acc += dbeta;
+    if (d_rgb) {
+      __syncwarp();
+      float* o = d_rgb + ray * S * 3;
+      for (int i = lane; i < S * 3; i += 32) {
+        int e = i / 3, ch = i - 3 * e;
+        float g = (ch == 0) ? gr : ((ch == 1) ? gg : gb);
+        o[i] = sm.w[warp][e] * g;
+      }
+    }
+    __syncwarp();
+  }
+  if (!abs_d && d_beta_param) {
+    dbeta_acc = warp_sum(dbeta_acc);
+    if (lane == 0 && dbeta_acc != 0.f) {
+      float sg = (__ldg(beta_param) > 0.f) ? 1.f : ((__ldg(beta_param) < 0.f) ? -1.f : 0.f);
+      atomicAdd(d_beta_param, sg * dbeta_acc);
+    }
+  }
+}
+
+static int comp_grid(int64_t R) {
+  int64_t blocks = cdiv(R, kCompWarps);
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace svs
+
+using namespace svs;
+
+#define DISPATCH_C(S, CALL)                       \
+  if ((S) <= 32) { constexpr int C = 1; CALL; }   \
+  else if ((S) <= 64) { constexpr int C = 2; CALL; } \
+  else if ((S) <= 128) { constexpr int C = 4; CALL; } \
+  else { constexpr int C = 8; CALL; }
+
+extern "C" int svs_composite_forward(const float* z, const float* sdf, const float* rgb, const float* normals,
+                                     const float* beta_param, float beta_min, const float* depth_scale,
+                                     const float* z_max, int64_t R, int32_t S, int32_t flags, float* weights,
+                                     float* rgb_values, float* depth_values, float* normal_map, float* bg_trans,
+                                     void* stream) {
+  SVS_CHECK_ARG(R >= 0 && S >= 1 && S <= 256, "svs_composite_forward: need 1 <= S <= 256 (got %d)", S);
+  SVS_CHECK_ARG(z && sdf && weights, "svs_composite_forward: z/sdf/weights required");
+  SVS_CHECK_ARG((flags & SVS_COMP_ABS_DENSITY) || beta_param, "svs_composite_forward: beta_param required");
+  SVS_CHECK_ARG(!(flags & SVS_COMP_ZMAX_TAIL) || z_max, "svs_composite_forward: z_max required");
+  SVS_CHECK_ARG(!normal_map || normals, "svs_composite_forward: normals required for normal_map");
+  SVS_CHECK_ARG(!rgb_values || rgb, "svs_composite_forward: rgb required for rgb_values");
+  if (R == 0) return SVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_C(S, (composite_fwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                    z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                    rgb_values, depth_values, normal_map, bg_trans)));
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
+extern "C" int svs_composite_backward(const float* z, const float* sdf, const float* rgb, const float* beta_param,
+                                      float beta_min, const float* depth_scale, const float* z_max, int64_t R,
+                                      int32_t S, int32_t flags, const float* d_rgb_values,
+                                      const float* d_depth_values, const float* d_weights,
+                                      const float* d_bg_trans, float* d_sdf, float* d_rgb, float* d_beta_param,
+                                      void* stream) {
+  SVS_CHECK_ARG(R >= 0 && S >= 1 && S <= 256, "svs_composite_backward: need 1 <= S <= 256 (got %d)", S);
+  SVS_CHECK_ARG(z && sdf && d_sdf, "svs_composite_backward: z/sdf/d_sdf required");
+  SVS_CHECK_ARG((flags & SVS_COMP_ABS_DENSITY) || beta_param, "svs_composite_backward: beta_param required");
+  SVS_CHECK_ARG(!(flags & SVS_COMP_ZMAX_TAIL) || z_max, "svs_composite_backward: z_max required");
+  SVS_CHECK_ARG(!d_rgb || rgb, "svs_composite_backward: rgb required for d_rgb");
+  if (R == 0) return SVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_C(S, (composite_bwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                    z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
+                    d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
