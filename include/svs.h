@@ -111,6 +111,9 @@ int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const flo
                              const float* d_grad, float* dwbuf, float* ws, int engine, void* stream);
 int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P);
 
+/* Positional encoding on its own (embedder.py:10-36 `Embedder.embed`): x (P,d_in) -> out (P, d_in*(1+2*n_freqs)). */
+int svs_embed(const float* x, int64_t P, int32_t d_in, int32_t n_freqs, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Rendering network (RenderingNetwork.forward, network.py:170-190).
  *   idr : input = cat[points(3), PE(view_dirs), normals(3), feat(F)];  nerf: cat[PE(view_dirs), feat(F)].
@@ -208,6 +211,15 @@ int svs_composite_backward(const float* z, const float* sdf, const float* rgb, c
                            int32_t S, int32_t flags, const float* d_rgb_values, const float* d_depth_values,
                            const float* d_weights, const float* d_bg_trans, float* d_sdf, float* d_rgb,
                            float* d_beta_param, void* stream);
+
+/* Stand-alone density modules (density.py:16-35): out = Laplace(sdf; beta) or |sdf|.  sdf is (R,S);
+ * beta is |*beta_param|+beta_min, or beta_rows[r] when beta_rows != NULL (the sampler's per-ray override).
+ * backward: d_sdf = d_out * dsigma/ds ; *d_beta_param += sum d_out * dsigma/dbeta (only when beta_rows == NULL). */
+int svs_density_forward(const float* sdf, int64_t R, int32_t S, const float* beta_param, float beta_min,
+                        const float* beta_rows, int32_t abs_density, float* out, void* stream);
+int svs_density_backward(const float* sdf, int64_t R, int32_t S, const float* beta_param, float beta_min,
+                         const float* beta_rows, int32_t abs_density, const float* d_out, float* d_sdf,
+                         float* d_beta_param, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,8 +26,10 @@ OUT = os.path.join(ROOT, 'tests', 'golden')
 class Capture(object):
     """Wraps torch.searchsorted / torch.sort while the reference runs and records their index outputs."""
 
-    def __init__(self):
-        self.inds, self.sort_idx = [], []
+    def __init__(self, model=None):
+        self.inds, self.sort_idx, self.cdf, self.sort_in = [], [], [], []
+        self.model = model
+        self.dens_beta, self.bounds = [], []
 
     def __enter__(self):
         self._ss, self._sort = torch.searchsorted, torch.sort
@@ -35,18 +37,36 @@ class Capture(object):
         def ss(*a, **k):
             r = self._ss(*a, **k)
             self.inds.append(r.clone())
+            self.cdf.append(a[0].clone())
             return r
 
         def srt(*a, **k):
             r = self._sort(*a, **k)
             self.sort_idx.append(r[1].clone())
+            self.sort_in.append(a[0].clone())
             return r
 
         torch.searchsorted, torch.sort = ss, srt
+        if self.model is not None:   # per-iteration sampler state, recorded through hooks (no source change)
+            def dens_hook(mod, args, kwargs):
+                if kwargs.get('beta', None) is not None:
+                    self.dens_beta.append(kwargs['beta'].detach().clone())
+            self._h = self.model.density.register_forward_pre_hook(dens_hook, with_kwargs=True)
+            smp = self.model.ray_sampler
+            self._orig_bound = smp.get_error_bound
+
+            def bound(beta, mdl, sdf, z_vals, dists, d_star):
+                self.bounds.append((z_vals.detach().clone(), d_star.detach().clone(),
+                                    sdf.detach().reshape(z_vals.shape).clone()))
+                return self._orig_bound(beta, mdl, sdf, z_vals, dists, d_star)
+            smp.get_error_bound = bound
         return self
 
     def __exit__(self, *exc):
         torch.searchsorted, torch.sort = self._ss, self._sort
+        if self.model is not None:
+            self._h.remove()
+            del self.model.ray_sampler.get_error_bound
 
 
 def param_checksum(model):
@@ -75,7 +95,7 @@ def build(ns, kind, perturb, beta):
     else:
         model = ns.network_bg.VolSDFNetworkBG(C.bmvs_model_conf())
     if perturb or beta is not None:
-        S.perturb_(model, seed=7, w_std=0.02 if perturb else 0.0, b_std=0.01 if perturb else 0.0, beta=beta)
+        S.perturb_(model, seed=7, w_std=S.PERTURB_W if perturb else 0.0, b_std=S.PERTURB_B if perturb else 0.0, beta=beta)
     return model
 
 
@@ -87,7 +107,7 @@ def run_case(ns, name, kind, n_rays, training, perturb=False, beta=None, fast=No
     cs = param_checksum(model)
     rec['meta/param_sum'], rec['meta/param_abs_sum'] = cs
     torch.manual_seed(123)
-    with Capture() as cap:
+    with Capture(model) as cap:
         if training:
             model.train()
             out = model(inp, fast=1)
@@ -101,6 +121,18 @@ def run_case(ns, name, kind, n_rays, training, perturb=False, beta=None, fast=No
     for i, t in enumerate(cap.sort_idx):
         rec['sampler/sort_idx_%d' % i] = t.numpy().astype(np.int32)
     rec['sampler/n_searchsorted'] = len(cap.inds)
+    for i, t in enumerate(cap.cdf):
+        rec['sampler/cdf_%d' % i] = t.numpy()
+    for i, t in enumerate(cap.sort_in):
+        rec['sampler/sort_in_%d' % i] = t.numpy()
+    n_it = len(cap.inds)
+    per = len(cap.bounds) // max(n_it, 1)          # 1 + beta_iters error-bound calls per iteration
+    assert per * n_it == len(cap.bounds) and len(cap.dens_beta) == (per + 1) * n_it
+    for i in range(n_it):
+        z_i, dstar_i, sdf_i = cap.bounds[per * i]
+        rec['sampler/z_%d' % i], rec['sampler/d_star_%d' % i], rec['sampler/sdf_%d' % i] = \
+            z_i.numpy(), dstar_i.numpy(), sdf_i.numpy()
+        rec['sampler/beta_%d' % i] = cap.dens_beta[(per + 1) * i + per].reshape(-1).numpy()
     if training:
         gt = S.gt_rgb(n_rays)
         rgb_loss = (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean()
@@ -176,7 +208,7 @@ def main():
     run_case(ns, 'dtu_eval_r32_beta001', 'dtu', 32, False, perturb=True, beta=0.01)
     run_case(ns, 'dtu_train_r64', 'dtu', 64, True)
     run_case(ns, 'dtu_train_r64_pert', 'dtu', 64, True, perturb=True, beta=0.02)
-    run_case(ns, 'bmvs_eval_r32', 'bmvs', 32, False, perturb=True)
+    run_case(ns, 'bmvs_eval_r32', 'bmvs', 32, False, perturb=True, beta=0.02)
     run_case(ns, 'bmvs_train_r32', 'bmvs', 32, True, perturb=True)
 
 

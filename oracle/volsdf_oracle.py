@@ -326,7 +326,7 @@ def error_bound(beta, sdf, dists, d_star):
 def stable_merge(z_old, samples):
     """sort(cat[z, samples]) with ties kept in concatenation order (ray_sampler.py:189-190)."""
     cat = torch.cat([z_old, samples], -1)
-    z, idx = torch.sort(cat, -1, stable=True)
+    z, idx = torch.sort(cat, dim=-1, stable=True)
     return z, idx
 
 
@@ -339,6 +339,57 @@ class SamplerTrace(object):
         self.z_eik = None
         self.z_bg = None
         self.sdf_evals = []      # number of rows x new samples evaluated per iteration
+
+
+def sampler_bound_step(z, sdf, beta_in, beta0, eps, beta_iters):
+    """d* and the beta line search of one iteration (ray_sampler.py:96-123) -> beta (R,), d_star (R,n-1)."""
+    R = z.shape[0]
+    dists = z[:, 1:] - z[:, :-1]
+    d_star = d_star_bound(z, sdf)
+    err = error_bound(beta0, sdf, dists, d_star)
+    beta = torch.where(err <= eps, beta0.expand_as(beta_in), beta_in)
+    bmin, bmax = beta0.expand(R).clone(), beta.clone()
+    for _ in range(beta_iters):
+        mid = (bmin + bmax) / 2.
+        err = error_bound(mid.unsqueeze(-1), sdf, dists, d_star)
+        bmax = torch.where(err <= eps, mid, bmax)
+        bmin = torch.where(err > eps, mid, bmin)
+    return bmax, d_star
+
+
+def sampler_resample_step(z, sdf, beta, d_star, cont, u, add_tiny):
+    """weights -> pdf -> cdf -> inverse CDF of one iteration (ray_sampler.py:126-185).
+    Returns cdf (R,n), inds (R,N), samples (R,N)."""
+    R, n = z.shape
+    f32 = z.dtype
+    dists = z[:, 1:] - z[:, :-1]
+    density = laplace_density(sdf, beta.unsqueeze(-1), canonical=True)
+    dists_p = torch.cat([dists, torch.full((R, 1), 1e10, dtype=f32)], -1)
+    fe = dists_p * density
+    sfe = torch.cat([torch.zeros(R, 1, dtype=f32), fe[:, :-1]], -1)
+    alpha = 1 - _exp(-fe)
+    trans = _exp(-_cumsum(sfe))
+    weights = alpha * trans
+    if cont:
+        b = beta.unsqueeze(-1)
+        eps_sec = _exp(-d_star / b) * (dists * dists) / (4 * b * b)
+        bo = (torch.clamp(_exp(_cumsum(eps_sec)), max=1.e6) - 1.0) * trans[:, :-1]
+        pdf = bo + add_tiny
+    else:
+        pdf = weights[:, :-1] + 1e-5
+    pdf = pdf / _rowsum(pdf)
+    cdf = torch.cat([torch.zeros(R, 1, dtype=f32), _cumsum(pdf)], -1)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=n - 1)
+    cb, ca = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    zb, za = torch.gather(z, 1, below), torch.gather(z, 1, above)
+    denom = ca - cb
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cb) / denom
+    samples = zb + t * (za - zb)
+    return cdf, inds, samples
 
 
 def sampler_get_z_vals(ray_dirs, cam_loc, sdf_fn, beta0, *, training, near, scene_radius, n_samples,
@@ -375,52 +426,16 @@ def sampler_get_z_vals(ray_dirs, cam_loc, sdf_fn, beta0, *, training, near, scen
         else:
             sdf = s_new
         n = z.shape[1]
-        dists = z[:, 1:] - z[:, :-1]
-        d_star = d_star_bound(z, sdf)
-        err = error_bound(beta0, sdf, dists, d_star)
-        beta = torch.where(err <= eps, beta0.expand_as(beta), beta)
-        bmin, bmax = beta0.expand(R).clone(), beta.clone()
-        for _ in range(beta_iters):
-            mid = (bmin + bmax) / 2.
-            err = error_bound(mid.unsqueeze(-1), sdf, dists, d_star)
-            bmax = torch.where(err <= eps, mid, bmax)
-            bmin = torch.where(err > eps, mid, bmin)
-        beta = bmax
-        density = laplace_density(sdf, beta.unsqueeze(-1), canonical=True)
-        dists_p = torch.cat([dists, torch.full((R, 1), 1e10, dtype=f32)], -1)
-        fe = dists_p * density
-        sfe = torch.cat([torch.zeros(R, 1, dtype=f32), fe[:, :-1]], -1)
-        alpha = 1 - _exp(-fe)
-        trans = _exp(-_cumsum(sfe))
-        weights = alpha * trans
+        beta, d_star = sampler_bound_step(z, sdf, beta, beta0, eps, beta_iters)
         total += 1
         not_conv = bool(beta.max() > beta0)
         cont = not_conv and total < max_iters
-        if cont:
-            N = n_samples_eval
-            b = beta.unsqueeze(-1)
-            eps_sec = _exp(-d_star / b) * (dists * dists) / (4 * b * b)
-            bo = (torch.clamp(_exp(_cumsum(eps_sec)), max=1.e6) - 1.0) * trans[:, :-1]
-            pdf = bo + add_tiny
-        else:
-            N = n_samples
-            pdf = weights[:, :-1] + 1e-5
-        pdf = pdf / _rowsum(pdf)
-        cdf = torch.cat([torch.zeros(R, 1, dtype=f32), _cumsum(pdf)], -1)
+        N = n_samples_eval if cont else n_samples
         if cont or not training:
             u = torch.linspace(0., 1., steps=N).unsqueeze(0).repeat(R, 1)
         else:
             u = rng['u_final']
-        u = u.contiguous()
-        inds = torch.searchsorted(cdf, u, right=True)
-        below = torch.clamp(inds - 1, min=0)
-        above = torch.clamp(inds, max=n - 1)
-        cb, ca = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
-        zb, za = torch.gather(z, 1, below), torch.gather(z, 1, above)
-        denom = ca - cb
-        denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-        t = (u - cb) / denom
-        samples = zb + t * (za - zb)
+        cdf, inds, samples = sampler_resample_step(z, sdf, beta, d_star, cont, u, add_tiny)
         it = {'n': n, 'beta': beta.clone(), 'inds': inds.clone(), 'samples': samples.clone(),
               'not_converge': not_conv, 'cont': cont, 'z': z.clone(), 'sdf': sdf.clone(), 'cdf': cdf.clone()}
         if cont:

@@ -299,6 +299,46 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   }
 }
 
+// stand-alone density modules (density.py:16-35)
+__global__ void density_fwd_kernel(const float* __restrict__ sdf, int64_t n, int S, const float* __restrict__ beta_param,
+                                   float beta_min, const float* __restrict__ beta_rows, int abs_d,
+                                   float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float beta = abs_d ? 1.f : (beta_rows ? beta_rows[i / S] : beta_of(beta_param, beta_min));
+  float em;
+  out[i] = density_fwd(sdf[i], beta, abs_d, &em);
+}
+
+__global__ void density_bwd_kernel(const float* __restrict__ sdf, int64_t n, int S, const float* __restrict__ beta_param,
+                                   float beta_min, const float* __restrict__ beta_rows, int abs_d,
+                                   const float* __restrict__ d_out, float* __restrict__ d_sdf,
+                                   float* __restrict__ d_beta_param) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float dbeta = 0.f;
+  if (i < n) {
+    float s = sdf[i], g = d_out[i];
+    float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+    if (abs_d) {
+      d_sdf[i] = g * sg;
+    } else {
+      float beta = beta_rows ? beta_rows[i / S] : beta_of(beta_param, beta_min);
+      float em;
+      float sigma = density_fwd(s, beta, false, &em);
+      float e = em + 1.0f;
+      d_sdf[i] = -g * (sg * sg) * e / (2.0f * beta * beta);
+      dbeta = g * (-sigma / beta + s * e / (2.0f * beta * beta * beta));
+    }
+  }
+  if (!abs_d && !beta_rows && d_beta_param) {
+    dbeta = warp_sum(dbeta);
+    if ((threadIdx.x & 31) == 0 && dbeta != 0.f) {
+      float bp = __ldg(beta_param);
+      atomicAdd(d_beta_param, ((bp > 0.f) ? 1.f : ((bp < 0.f) ? -1.f : 0.f)) * dbeta);
+    }
+  }
+}
+
 static int comp_grid(int64_t R) {
   int64_t blocks = cdiv(R, kCompWarps);
   int64_t cap = (int64_t)kNumSMs * 16;
@@ -351,6 +391,31 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   DISPATCH_C(S, (composite_bwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
                     z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                     d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
+extern "C" int svs_density_forward(const float* sdf, int64_t R, int32_t S, const float* beta_param, float beta_min,
+                                   const float* beta_rows, int32_t abs_density, float* out, void* stream) {
+  SVS_CHECK_ARG(sdf && out && R >= 0 && S >= 1, "svs_density_forward: bad arguments");
+  SVS_CHECK_ARG(abs_density || beta_rows || beta_param, "svs_density_forward: beta required");
+  int64_t n = R * S;
+  if (n == 0) return SVS_OK;
+  density_fwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(sdf, n, S, beta_param, beta_min,
+                                                                              beta_rows, abs_density, out);
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
+extern "C" int svs_density_backward(const float* sdf, int64_t R, int32_t S, const float* beta_param, float beta_min,
+                                    const float* beta_rows, int32_t abs_density, const float* d_out, float* d_sdf,
+                                    float* d_beta_param, void* stream) {
+  SVS_CHECK_ARG(sdf && d_out && d_sdf && R >= 0 && S >= 1, "svs_density_backward: bad arguments");
+  SVS_CHECK_ARG(abs_density || beta_rows || beta_param, "svs_density_backward: beta required");
+  int64_t n = R * S;
+  if (n == 0) return SVS_OK;
+  density_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      sdf, n, S, beta_param, beta_min, beta_rows, abs_density, d_out, d_sdf, d_beta_param);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

@@ -425,6 +425,15 @@ extern "C" int svs_mlp_param_grads(const svs_mlp_desc* d, const svs_mlp_params* 
   return SVS_OK;
 }
 
+extern "C" int svs_embed(const float* x, int64_t P, int32_t d_in, int32_t n_freqs, float* out, void* stream) {
+  SVS_CHECK_ARG(x && out && P >= 0 && d_in >= 1 && d_in <= 4 && n_freqs >= 0 && n_freqs <= 16, "svs_embed: bad arguments");
+  if (P == 0) return SVS_OK;
+  int w = d_in * (1 + 2 * n_freqs);
+  pe_kernel<<<blocks_for(P * w), 256, 0, (cudaStream_t)stream>>>(x, P, d_in, n_freqs, out, w, 0, 1.f, w);
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // SDF network
 // ---------------------------------------------------------------------------------------------------

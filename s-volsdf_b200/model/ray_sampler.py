@@ -1,0 +1,206 @@
+"""UniformSampler / ErrorBoundSampler with the reference's interface (volsdf/model/ray_sampler.py).
+
+The Python side only owns the outer loop of Algorithm 1 (each iteration needs the SDF network) and the
+reference's CPU random draws; every per-ray computation runs in the warp-per-ray kernels of
+csrc/sampler.cu.  Training (`fast=1`) has no host synchronisation at all; evaluation reads one 4-byte
+convergence flag per iteration (the reference synchronises ~47 times per iteration).
+"""
+import abc
+
+import torch
+
+from .. import _lib as L
+from .. import functional as F
+from .._lib import ptr
+
+
+class RefRng(object):
+    """The reference's random draws: CPU default generator, same shapes, same order,
+    staged through pinned memory so the host->device copies never block the stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.h2d_bytes = 0
+
+    def _up(self, t):
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t.to(self.device, non_blocking=True)
+
+    def rand(self, *shape):
+        return self._up(torch.rand(shape, pin_memory=True))
+
+    def randperm(self, n):
+        return self._up(torch.randperm(n, pin_memory=True).to(torch.int32))
+
+    def randint(self, high, shape):
+        return self._up(torch.randint(high, shape, pin_memory=True))
+
+    def uniform(self, shape, lo, hi):
+        return self._up(torch.empty(shape, pin_memory=True).uniform_(lo, hi))
+
+
+_const_cache = {}
+
+
+def _linspace(n, device):
+    key = ('lin', n, str(device))
+    if key not in _const_cache:
+        _const_cache[key] = torch.linspace(0., 1., steps=n).to(device)   # CPU linspace, as the reference
+    return _const_cache[key]
+
+
+def _extra_idx_eval(n, k, device):
+    key = ('extra', n, k, str(device))
+    if key not in _const_cache:
+        _const_cache[key] = torch.linspace(0, n - 1, k).long().to(torch.int32).to(device)
+    return _const_cache[key]
+
+
+class RaySampler(metaclass=abc.ABCMeta):
+    def __init__(self, near, far):
+        self.near = near
+        self.far = far
+
+    @abc.abstractmethod
+    def get_z_vals(self, ray_dirs, cam_loc, model):
+        pass
+
+
+def _cfg(near, far, eps=0.1, add_tiny=0.0, beta_iters=10, exact=True):
+    c = L.SamplerCfg()
+    c.near, c.far, c.eps, c.add_tiny = float(near), float(far), float(eps), float(add_tiny)
+    # 1/(4*log(1+eps)) exactly as ray_sampler.py:77 evaluates it (fp32 tensor ops on the host)
+    c.inv4logeps = float(1.0 / (4.0 * torch.log(torch.tensor(eps + 1.0))))
+    c.beta_iters, c.exact = int(beta_iters), 1 if exact else 0
+    return c
+
+
+class UniformSampler(RaySampler):
+    """ray_sampler.py:15-43"""
+
+    def __init__(self, scene_bounding_sphere, near, N_samples, take_sphere_intersection=False, far=-1):
+        super().__init__(near, 2.0 * scene_bounding_sphere if far == -1 else far)
+        self.N_samples = N_samples
+        self.scene_bounding_sphere = scene_bounding_sphere
+        self.take_sphere_intersection = take_sphere_intersection
+
+    def get_z_vals(self, ray_dirs, cam_loc, model, iter_step=None, _rng=None, _far_ray=None, _want_beta=False):
+        R = ray_dirs.shape[0]
+        dev = ray_dirs.device
+        far_ray = _far_ray
+        if self.take_sphere_intersection and far_ray is None:
+            from ..utils import rend_util
+            far_ray = rend_util.get_sphere_intersections(cam_loc, ray_dirs, r=self.scene_bounding_sphere)[:, 1].contiguous()
+        cfg = _cfg(self.near, -1.0 if self.take_sphere_intersection else self.far)
+        n = self.N_samples
+        t_rand = None
+        if model.training:
+            rng = _rng or RefRng(dev)
+            t_rand = rng.rand(R, n)
+        z = torch.empty(R, n, dtype=torch.float32, device=dev)
+        beta = torch.empty(R, dtype=torch.float32, device=dev)
+        L.call('svs_sampler_init', cfg, R, n, ptr(_linspace(n, dev)), ptr(t_rand), ptr(far_ray), ptr(z), ptr(beta),
+               L.stream())
+        return (z, beta) if _want_beta else z
+
+
+class ErrorBoundSampler(RaySampler):
+    """VolSDF Algorithm 1 (ray_sampler.py:46-229)."""
+
+    def __init__(self, scene_bounding_sphere, near, N_samples, N_samples_eval, N_samples_extra,
+                 eps, beta_iters, max_total_iters,
+                 inverse_sphere_bg=False, N_samples_inverse_sphere=0, add_tiny=0.0):
+        super().__init__(near, 2.0 * scene_bounding_sphere)
+        self.N_samples = N_samples
+        self.N_samples_eval = N_samples_eval
+        self.uniform_sampler = UniformSampler(scene_bounding_sphere, near, N_samples_eval,
+                                              take_sphere_intersection=inverse_sphere_bg)
+        self.N_samples_extra = N_samples_extra
+        self.eps = eps
+        self.beta_iters = beta_iters
+        self.max_total_iters = max_total_iters
+        self.scene_bounding_sphere = scene_bounding_sphere
+        self.add_tiny = add_tiny
+        self.inverse_sphere_bg = inverse_sphere_bg
+        if inverse_sphere_bg:
+            self.inverse_sphere_sampler = UniformSampler(1.0, 0.0, N_samples_inverse_sphere, False, far=1.0)
+        self.exact = True          # fp64 transcendentals + fp64 scans (bit-exact vs the oracle)
+        self.trace = None          # set to a list to record per-iteration tensors (tests)
+        self.last_iters = 0
+
+    def get_z_vals(self, ray_dirs, cam_loc, model, fast=-1, iter_step=None, _rng=None, _sdf_fn=None):
+        R = ray_dirs.shape[0]
+        dev = ray_dirs.device
+        ray_dirs = ray_dirs.detach().contiguous().float()
+        cam_loc = cam_loc.detach().contiguous().float()
+        max_total_iters = fast if fast >= 0 else self.max_total_iters
+        rng = _rng or RefRng(dev)
+        training = model.training
+        beta_param = model.density.beta.detach().reshape(1)
+        beta_min = float(model.density.beta_min)
+        sdf_fn = _sdf_fn or model.implicit_network.get_sdf_vals
+
+        far_ray = None
+        if self.inverse_sphere_bg:
+            from ..utils import rend_util
+            far_ray = rend_util.get_sphere_intersections(cam_loc, ray_dirs, r=self.scene_bounding_sphere)[:, 1].contiguous()
+        cfg = _cfg(self.near, -1.0 if self.inverse_sphere_bg else self.far, self.eps, self.add_tiny,
+                   self.beta_iters, self.exact)
+
+        # uniform start + Lemma-2 beta (ray_sampler.py:72-78)
+        z, beta = self.uniform_sampler.get_z_vals(ray_dirs, cam_loc, model, iter_step=iter_step, _rng=rng,
+                                                  _far_ray=far_ray, _want_beta=True)
+        samples, samples_idx, sdf = z, None, None
+        total_iters, not_converge = 0, True
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = L.stream()
+        while not_converge and total_iters < max_total_iters:
+            n, n_new = z.shape[1], samples.shape[1]
+            pts = F.ray_points(cam_loc, ray_dirs, samples).reshape(-1, 3)
+            with torch.no_grad():
+                sdf_new = sdf_fn(pts).reshape(R, n_new).contiguous()
+            sdf_m = torch.empty(R, n, dtype=torch.float32, device=dev)
+            flag.zero_()
+            L.call('svs_sampler_bound', cfg, R, n, n_new, ptr(z), ptr(sdf), ptr(sdf_new), ptr(samples_idx), ptr(sdf_m),
+                   ptr(beta_param), beta_min, ptr(beta), ptr(flag), st)
+            sdf = sdf_m
+            total_iters += 1
+            if total_iters < max_total_iters:
+                not_converge = bool(flag.item())   # the only host sync; never reached when fast=1 (training)
+            cont = not_converge and total_iters < max_total_iters
+            n_u = self.N_samples_eval if cont else self.N_samples
+            if cont or not training:
+                u, per_ray = _linspace(n_u, dev), 0
+            else:
+                u, per_ray = rng.rand(R, n_u), 1
+            samples = torch.empty(R, n_u, dtype=torch.float32, device=dev)
+            inds = torch.empty(R, n_u, dtype=torch.int32, device=dev) if self.trace is not None else None
+            z_m = torch.empty(R, n + n_u, dtype=torch.float32, device=dev) if cont else None
+            sidx = torch.empty(R, n + n_u, dtype=torch.int32, device=dev) if cont else None
+            L.call('svs_sampler_resample', cfg, R, n, n_u, 1 if cont else 0, ptr(z), ptr(sdf), ptr(beta), ptr(u), per_ray,
+                   ptr(samples), ptr(inds), ptr(z_m), ptr(sidx), st)
+            if self.trace is not None:
+                self.trace.append({'n': n, 'z': z, 'sdf': sdf, 'beta': beta.clone(), 'inds': inds, 'samples': samples,
+                                   'samples_idx': sidx, 'cont': cont})
+            if cont:
+                z, samples_idx = z_m, sidx
+        self.last_iters = total_iters
+
+        # final sample set (ray_sampler.py:193-212)
+        n = z.shape[1]
+        n_extra = self.N_samples_extra
+        extra_idx = None
+        if n_extra > 0:
+            extra_idx = rng.randperm(n)[:n_extra].contiguous() if training else _extra_idx_eval(n, n_extra, dev)
+        n_s = samples.shape[1]
+        m = n_s + 2 + n_extra
+        z_final = torch.empty(R, m, dtype=torch.float32, device=dev)
+        z_eik = torch.empty(R, 1, dtype=torch.float32, device=dev)
+        eik_idx = rng.randint(m, (R,))
+        L.call('svs_sampler_finalize', cfg, R, n, n_s, ptr(z), ptr(samples.contiguous()), ptr(extra_idx), n_extra,
+               ptr(far_ray), ptr(eik_idx), ptr(z_final), ptr(z_eik), st)
+        if self.inverse_sphere_bg:
+            z_bg = self.inverse_sphere_sampler.get_z_vals(ray_dirs, cam_loc, model, _rng=rng)
+            z_bg = z_bg * (1. / self.scene_bounding_sphere)
+            return (z_final, z_bg), z_eik
+        return z_final, z_eik

@@ -79,7 +79,10 @@ def gt_rgb(n_rays, seed=2):
     return torch.rand(1, n_rays, 3, generator=g)
 
 
-def perturb_(model, seed=7, w_std=0.02, b_std=0.01, beta=None):
+PERTURB_W, PERTURB_B = 0.004, 0.002   # small enough to keep the geometric-init sphere a surface
+
+
+def perturb_(model, seed=7, w_std=PERTURB_W, b_std=PERTURB_B, beta=None):
     """"Trained-like" variant of a freshly initialised model (in place, deterministic).
 
     Geometric init leaves the positional-encoding columns of lin0 and the skip columns of lin4 at zero

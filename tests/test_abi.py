@@ -1,0 +1,55 @@
+"""The C-ABI library loads and exports exactly the symbols include/svs.h declares (no compute calls)."""
+import os
+import re
+
+import svolsdf_b200._lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'svs.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(svs_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_entry_points():
+    syms = header_symbols()
+    assert 'svs_sdf_outputs_backward' in syms and 'svs_composite_forward' in syms
+    assert len(syms) >= 30
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    for name in header_symbols():
+        assert hasattr(lib, name), 'missing export: ' + name
+
+
+def test_ctypes_table_matches_header():
+    assert sorted(L.SIGNATURES.keys()) == header_symbols()
+
+
+def test_abi_version_and_engine_query():
+    lib = L.load()
+    assert lib.svs_abi_version() == 1
+    assert lib.svs_has_engine(L.ENGINE_FP32) == 1
+
+
+def test_descriptor_validation_needs_no_gpu():
+    lib = L.load()
+    d = L.make_desc(L.NET_SDF, [39, 256, 256, 256, 256, 256, 256, 256, 256],
+                    [256, 256, 256, 217, 256, 256, 256, 256, 257], d_in=3, n_freqs=6, skip_layer=4)
+    n = lib.svs_mlp_wbuf_floats(d)
+    assert n == sum(o * ((i + 3) // 4 * 4) + (o + 3) // 4 * 4 for i, o in
+                    zip([39, 256, 256, 256, 256, 256, 256, 256, 256], [256, 256, 256, 217, 256, 256, 256, 256, 257]))
+    assert lib.svs_sdf_ldy(d) == 260
+    bad = L.make_desc(L.NET_SDF, [39, 256], [256, 257], d_in=3, n_freqs=5)
+    assert lib.svs_mlp_wbuf_floats(bad) == -1
+    assert b'PE width' in lib.svs_last_error()
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    with pytest.raises(L.SvsError):
+        L.ptr(torch.zeros(4))
