@@ -561,7 +561,7 @@ def volsdf_loss(out, rgb_gt, eikonal_weight=0.1):
 # --------------------------------------------------------------------------------------------
 
 
-def volsdf_bg_forward(sd, conf, inp, training, fast=-1, rng=None, dtype=torch.float32):
+def volsdf_bg_forward(sd, conf, inp, training, fast=-1, rng=None, dtype=torch.float32, z_override=None):
     imp = conf.get_config('implicit_network')
     rnd = conf.get_config('rendering_network')
     smp = conf.get_config('ray_sampler')
@@ -585,13 +585,16 @@ def volsdf_bg_forward(sd, conf, inp, training, fast=-1, rng=None, dtype=torch.fl
         with torch.no_grad():
             return sdf_vals(sd32, 'implicit_network', p, multires, 0.0, 1.0)
 
-    (z_all, z_bg), z_eik, trace = sampler_get_z_vals(
-        dirs, cam, sdf_fn, beta0, training=training, near=float(smp['near']), scene_radius=radius,
-        n_samples=int(smp['N_samples']), n_samples_eval=int(smp['N_samples_eval']),
-        n_samples_extra=int(smp['N_samples_extra']), eps=float(smp['eps']),
-        beta_iters=int(smp['beta_iters']), max_total_iters=int(smp['max_total_iters']), fast=fast, rng=rng,
-        inverse_sphere_bg=True, n_samples_inverse_sphere=int(smp['N_samples_inverse_sphere']),
-        add_tiny=float(smp.get('add_tiny', 0.0)))
+    if z_override is not None:
+        (z_all, z_bg), z_eik, trace = z_override
+    else:
+        (z_all, z_bg), z_eik, trace = sampler_get_z_vals(
+            dirs, cam, sdf_fn, beta0, training=training, near=float(smp['near']), scene_radius=radius,
+            n_samples=int(smp['N_samples']), n_samples_eval=int(smp['N_samples_eval']),
+            n_samples_extra=int(smp['N_samples_extra']), eps=float(smp['eps']),
+            beta_iters=int(smp['beta_iters']), max_total_iters=int(smp['max_total_iters']), fast=fast, rng=rng,
+            inverse_sphere_bg=True, n_samples_inverse_sphere=int(smp['N_samples_inverse_sphere']),
+            add_tiny=float(smp.get('add_tiny', 0.0)))
     sdd = {k: v.to(dtype) for k, v in sd.items()}
     cam_c, dirs_c = cam.to(dtype), dirs.to(dtype)
     z_max = z_all[:, -1].to(dtype)

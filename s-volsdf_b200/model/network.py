@@ -211,6 +211,7 @@ class VolSDFNetwork(nn.Module):
         self.last_rng = rng
         z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, fast=fast, iter_step=iter_step,
                                                             _rng=rng)
+        self.last_z = (z_vals, z_samples_eik)    # kept for parity tests (inject the same samples into the oracle)
         S = z_vals.shape[1]
         points = F.ray_points(cam_loc, ray_dirs, z_vals)               # (R,S,3)
         points_flat = points.reshape(-1, 3)

@@ -52,6 +52,7 @@ class VolSDFNetworkBG(nn.Module):
         rng = RefRng(dev)
         self.last_rng = rng
         (z_all, z_vals_bg), z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, fast=fast, _rng=rng)
+        self.last_z = ((z_all, z_vals_bg), z_samples_eik)
         z_max = z_all[:, -1].contiguous()
         z_vals = z_all[:, :-1].contiguous()
         S = z_vals.shape[1]

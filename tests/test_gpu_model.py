@@ -1,0 +1,227 @@
+"""GPU parity at the sampler boundary (bit-exact) and at the model boundary (reference outputs / gradients)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_model, conf_of, load_golden, max_abs, model_from_golden, rel_err, state_dict_cpu
+from oracle import volsdf_oracle as O
+import svolsdf_b200.scene as S
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _to_dev(inp):
+    return {k: v.to(DEV) for k, v in inp.items()}
+
+
+# ------------------------------------------------------------------------------------------------------
+# sampler: injected SDF -> bit-exact indices, counts and positions against the canonical-arithmetic oracle
+# ------------------------------------------------------------------------------------------------------
+
+def _sampler_case(kind, training, beta, R=96, fast=-1):
+    model = build_model(kind, perturb=True, beta=beta, device=DEV)
+    model.train(training)
+    sd = state_dict_cpu(model)
+    conf = conf_of(kind)
+    imp = conf.get_config('implicit_network')
+    radius = conf.get_float('scene_bounding_sphere')
+    sdf_radius = radius if kind == 'dtu' else 0.0
+    scale = float(imp.get('sphere_scale', 1.0))
+    inp = S.make_input(kind, R)
+    rd, cl = O.get_camera_params(inp['uv'], inp['pose'], inp['intrinsics'])
+    dirs, cam = rd[0].contiguous(), cl.expand(R, 3).contiguous()
+
+    def sdf_cpu(p):   # the SAME fp32 values are injected on both sides
+        with torch.no_grad():
+            return O.sdf_vals(sd, 'implicit_network', p, 6, sdf_radius, scale)
+
+    smp = conf.get_config('ray_sampler')
+    torch.manual_seed(77)
+    rng = O.draw_rng(R, training, bg=(kind == 'bmvs'), radius=radius)
+    beta0 = O.get_beta(sd['density.beta'], 0.0001)
+    ref = O.sampler_get_z_vals(
+        dirs, cam, sdf_cpu, beta0, training=training, near=float(smp['near']), scene_radius=radius,
+        n_samples=int(smp['N_samples']), n_samples_eval=int(smp['N_samples_eval']),
+        n_samples_extra=int(smp['N_samples_extra']), eps=float(smp['eps']), beta_iters=int(smp['beta_iters']),
+        max_total_iters=int(smp['max_total_iters']), fast=fast, rng=rng, inverse_sphere_bg=(kind == 'bmvs'),
+        n_samples_inverse_sphere=int(smp.get('N_samples_inverse_sphere', 0)), add_tiny=float(smp.get('add_tiny', 0.0)))
+    sampler = model.ray_sampler
+    sampler.trace = []
+    torch.manual_seed(77)   # the CUDA side draws the same CPU randoms itself, in the reference's order
+    got = sampler.get_z_vals(dirs.to(DEV), cam.to(DEV), model, fast=fast,
+                             _sdf_fn=lambda p: sdf_cpu(p.cpu()).to(DEV))
+    trace, sampler.trace = sampler.trace, None
+    return ref, got, trace
+
+
+@pytest.mark.parametrize('kind,training,beta,fast', [('dtu', False, 0.01, -1), ('dtu', False, None, -1),
+                                                     ('dtu', True, 0.02, 1), ('bmvs', False, 0.02, -1),
+                                                     ('bmvs', True, None, 1), ('dtu', False, 0.01, 2)])
+def test_sampler_bit_exact(kind, training, beta, fast):
+    (z_ref, z_eik_ref, tr), (z_got, z_eik_got), trace = _sampler_case(kind, training, beta, fast=fast)
+    assert len(trace) == len(tr.iters), 'iteration count'
+    for i, (a, b) in enumerate(zip(trace, tr.iters)):
+        assert a['n'] == b['n'], 'sample count in iteration %d' % i
+        assert torch.equal(a['z'].cpu(), b['z']), 'z in iteration %d' % i
+        assert torch.equal(a['sdf'].cpu(), b['sdf']), 'merged sdf in iteration %d' % i
+        assert torch.equal(a['beta'].cpu(), b['beta']), 'beta in iteration %d' % i
+        assert torch.equal(a['inds'].cpu().long(), b['inds']), 'searchsorted indices in iteration %d' % i
+        assert torch.equal(a['samples'].cpu(), b['samples']), 'samples in iteration %d' % i
+        assert a['cont'] == b['cont']
+        if b['cont']:
+            assert torch.equal(a['samples_idx'].cpu().long(), b['samples_idx']), 'sort indices in iteration %d' % i
+    if kind == 'bmvs':
+        assert torch.equal(z_got[0].cpu(), z_ref[0]) and torch.equal(z_got[1].cpu(), z_ref[1])
+    else:
+        assert torch.equal(z_got.cpu(), z_ref)
+    assert torch.equal(z_eik_got.cpu(), z_eik_ref)
+    if fast == -1 and not training and beta is not None:
+        assert len(trace) == 5    # small beta exercises every iteration (n = 128 ... 640)
+
+
+def test_sampler_fast_mode_close():
+    """exact=0 (fp32 intrinsics, fp32 scans) is the throughput mode: same counts, positions to ~1e-4."""
+    model = build_model('dtu', perturb=True, beta=0.01, device=DEV).eval()
+    inp = _to_dev(S.make_input('dtu', 128))
+    from svolsdf_b200 import functional as F
+    d, c, _ = F.raygen(inp['uv'][0], inp['pose'][0], inp['intrinsics'][0])
+    torch.manual_seed(5)
+    z1, _ = model.ray_sampler.get_z_vals(d, c, model)
+    it1 = model.ray_sampler.last_iters
+    model.ray_sampler.exact = False
+    torch.manual_seed(5)
+    z2, _ = model.ray_sampler.get_z_vals(d, c, model)
+    model.ray_sampler.exact = True
+    assert z1.shape == z2.shape and model.ray_sampler.last_iters == it1
+    assert float(((z1 - z2).abs() < 1e-3).float().mean()) > 0.97
+
+
+# ------------------------------------------------------------------------------------------------------
+# model forward / backward
+# ------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('name', ['dtu_eval_r64', 'dtu_eval_r32_beta001', 'bmvs_eval_r32'])
+def test_eval_forward_vs_reference_golden(name):
+    """End to end against the REFERENCE's recorded outputs (north_star: rgb/depth max-abs <= 1e-3, fp32 mode)."""
+    g = load_golden(name)
+    model = model_from_golden(g, DEV).eval()
+    kind, R = str(g['meta/kind']), int(g['meta/n_rays'])
+    torch.manual_seed(123)
+    out = model(_to_dev(S.make_input(kind, R)))
+    assert model.ray_sampler.last_iters == int(g['sampler/n_searchsorted'])
+    assert not out['rgb_values'].requires_grad
+    for k, tol in (('rgb_values', 1e-3), ('depth_values', 1e-3), ('normal_map', 1e-3)):
+        assert out[k].shape == g['out/' + k].shape
+        assert max_abs(out[k].cpu(), g['out/' + k]) < tol, (k, max_abs(out[k].cpu(), g['out/' + k]))
+    for k in ('weights', 'depth_vals', 'xyz'):
+        assert out[k].shape == g['out/' + k].shape
+    if kind == 'bmvs':
+        assert max_abs(out['depth_values_all'].cpu(), g['out/depth_values_all']) < 2e-3
+    assert abs(float(out['weights'].sum()) - float(g['out/weights'].sum())) < 1e-2 * R
+
+
+@pytest.mark.parametrize('name', ['dtu_train_r64', 'dtu_train_r64_pert', 'bmvs_train_r32'])
+def test_train_step_vs_reference_golden(name):
+    """Forward + VolSDFLoss + backward against the reference's recorded loss and gradient fingerprints."""
+    g = load_golden(name)
+    model = model_from_golden(g, DEV).train()
+    kind, R = str(g['meta/kind']), int(g['meta/n_rays'])
+    torch.manual_seed(123)
+    out = model(_to_dev(S.make_input(kind, R)), fast=1)
+    for k in ('rgb_values', 'depth_values', 'grad_theta'):
+        assert max_abs(out[k].detach().cpu(), g['out/' + k]) < 1e-3, (k, max_abs(out[k].detach().cpu(), g['out/' + k]))
+    gt = S.gt_rgb(R).to(DEV)
+    loss = (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean() + 0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+    assert abs(float(loss) - float(g['loss'])) < 2e-4
+    model.zero_grad()
+    loss.backward()
+    bad = []
+    for pname, p in model.named_parameters():
+        ref_norm = float(g['grad_norm/' + pname])
+        gr = (p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).double().cpu()
+        pick = torch.from_numpy(g['grad_pick_idx/' + pname])
+        ref_pick = torch.from_numpy(g['grad_pick/' + pname])
+        scale = ref_norm / np.sqrt(p.numel()) + float(ref_pick.abs().max())
+        err = float((gr[pick] - ref_pick).abs().max())
+        # north_star: parameter gradients to relative error <= 1e-2 (here in fp32 mode, typically 1e-3)
+        if abs(float(gr.norm()) - ref_norm) > 1e-2 * ref_norm + 1e-7 or err > 1e-2 * scale + 1e-8:
+            bad.append((pname, float(gr.norm()), ref_norm, err, scale))
+    assert not bad, bad[:6]
+
+
+@pytest.mark.parametrize('kind', ['dtu', 'bmvs'])
+def test_train_gradients_vs_fp64_oracle(kind):
+    """All parameter gradients of one train step against fp64 autograd on the oracle, same sample positions."""
+    R = 48
+    model = build_model(kind, perturb=True, beta=0.05, device=DEV).train()
+    sd = state_dict_cpu(model)
+    inp = S.make_input(kind, R)
+    torch.manual_seed(321)
+    out = model(_to_dev(inp), fast=1)
+    gt = S.gt_rgb(R)
+    loss = (out['rgb_values'] - gt.reshape(-1, 3).to(DEV)).abs().mean() + \
+        0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean() + 0.05 * out['weights'].pow(2).sum(1).mean() + \
+        0.1 * out['depth_values'].mean()
+    if kind == 'bmvs':
+        loss = loss + 0.1 * out['depth_values_all'].mean()
+    model.zero_grad()
+    loss.backward()
+    # oracle on the SAME z samples and the same eikonal points
+    ref = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    z, z_eik = model.last_z
+    torch.manual_seed(321)
+    rng = O.draw_rng(R, True, bg=(kind == 'bmvs'))
+    if kind == 'dtu':
+        zo = (z.cpu(), z_eik.cpu(), None)
+        o = O.volsdf_forward(ref, conf_of(kind), inp, True, fast=1, rng=rng, dtype=torch.float64, z_override=zo)
+    else:
+        zo = ((z[0].cpu(), z[1].cpu()), z_eik.cpu(), None)
+        o = O.volsdf_bg_forward(ref, conf_of(kind), inp, True, fast=1, rng=rng, dtype=torch.float64, z_override=zo)
+    rl = (o['rgb_values'] - gt.reshape(-1, 3).double()).abs().mean() + \
+        0.1 * ((o['grad_theta'].norm(2, dim=1) - 1) ** 2).mean() + 0.05 * o['weights'].pow(2).sum(1).mean() + \
+        0.1 * o['depth_values'].mean()
+    if kind == 'bmvs':
+        rl = rl + 0.1 * o['depth_values_all'].mean()
+    rl.backward()
+    for k in ('rgb_values', 'depth_values', 'weights', 'grad_theta'):
+        assert max_abs(out[k].detach().cpu(), o[k].detach()) < 2e-4, (k, max_abs(out[k].detach().cpu(), o[k].detach()))
+    assert abs(float(loss) - float(rl)) < 1e-4
+    rows = []
+    for name, p in model.named_parameters():
+        rg = ref[name].grad if ref[name].grad is not None else torch.zeros_like(ref[name])
+        og = p.grad if p.grad is not None else torch.zeros_like(p)
+        e = rel_err(og.cpu(), rg) if float(rg.norm()) > 1e-10 else float(og.norm())
+        rows.append((e, name, float(rg.norm())))
+    rows.sort(reverse=True)
+    assert rows[0][0] < 5e-3, rows[:6]
+
+
+def test_state_dict_roundtrip_and_optimizer_step():
+    """The reference's loop calls Adam(model.parameters()), clip_grad_norm_, state_dict()/load_state_dict()."""
+    model = build_model('dtu', device=DEV).train()
+    keys = list(model.state_dict().keys())
+    assert 'implicit_network.lin0.weight_g' in keys and 'rendering_network.lin4.bias' in keys and 'density.beta' in keys
+    assert sum(p.numel() for p in model.parameters()) == 797883
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    inp = _to_dev(S.make_input('dtu', 32))
+    gt = S.gt_rgb(32).to(DEV)
+    losses = []
+    for _ in range(3):
+        torch.manual_seed(1)
+        out = model(inp, fast=1)
+        loss = (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean() + 0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    m2 = build_model('dtu', device=DEV)
+    m2.load_state_dict(model.state_dict())
+    model.eval(), m2.eval()
+    torch.manual_seed(3)
+    a = model(inp)
+    torch.manual_seed(3)
+    b = m2(inp)
+    assert torch.equal(a['rgb_values'], b['rgb_values'])
