@@ -13,7 +13,9 @@ Written against plain torch CPU tensors (the reference's arithmetic IS torch's);
 parts use autograd in fp32 or fp64 as an independent check of the hand-derived CUDA backward, the
 sampler/compositor parts spell out a CANONICAL fp32 arithmetic that the CUDA "exact" mode reproduces
 bit-for-bit:
-  * +,-,*,/ and sqrt are IEEE fp32, evaluated in the reference's operator order, never fused;
+  * +,-,*,/ are IEEE fp32, evaluated in the reference's operator order, never fused;
+  * sqrt is the correctly rounded fp32 root (evaluated in fp64 and rounded: torch's vectorised CPU sqrtf is
+    1 ulp off for ~0.7% of inputs — measured — so it cannot serve as the canonical definition);
   * exp / expm1 are evaluated in fp64 and rounded once to fp32;
   * cumsum accumulates in fp64 and rounds every prefix to fp32 (what torch's CPU cumsum does);
   * row sums used for normalisation are the fp64 sum rounded to fp32 (== last cumsum element);
@@ -37,6 +39,10 @@ def _exp(x):
 
 def _expm1(x):
     return torch.expm1(x.double()).to(x.dtype)
+
+
+def _sqrt(x):
+    return torch.sqrt(x.double()).to(x.dtype)
 
 
 def _cumsum(x):
@@ -77,10 +83,11 @@ def get_camera_params(uv, pose, intrinsics):
 def get_sphere_intersections(cam_loc, ray_dirs, r):
     """(R,3),(R,3) -> (R,2) near/far; raises where the reference prints and exit()s (rend_util.py:209-211)."""
     dot = (ray_dirs * cam_loc).sum(-1, keepdim=True)
-    under = dot ** 2 - (cam_loc.norm(2, 1, keepdim=True) ** 2 - r ** 2)
+    on = _sqrt((cam_loc * cam_loc).sum(-1, keepdim=True))
+    under = dot ** 2 - (on ** 2 - r ** 2)
     if (under <= 0).sum() > 0:
         raise ValueError('BOUNDING SPHERE PROBLEM!')
-    out = torch.sqrt(under) * torch.tensor([-1.0, 1.0], dtype=under.dtype) - dot
+    out = _sqrt(under) * torch.tensor([-1.0, 1.0], dtype=under.dtype) - dot
     return out.clamp_min(0.0)
 
 
@@ -290,7 +297,7 @@ def beta_upper_bound(z, eps):
     dists = z[:, 1:] - z[:, :-1]
     coef = 1.0 / (4.0 * torch.log(torch.tensor(eps + 1.0)))
     bound = coef * _rowsum(dists * dists).squeeze(-1)
-    return torch.sqrt(bound)
+    return _sqrt(bound)
 
 
 def d_star_bound(z, d):
@@ -305,7 +312,7 @@ def d_star_bound(z, d):
     s = (a + b + c) / 2.0
     area = s * (s - a) * (s - b) * (s - c)
     mask = ~first & ~second & (b + c - a > 0)
-    tri = (2.0 * torch.sqrt(area)) / a
+    tri = (2.0 * _sqrt(area)) / a
     ds = torch.where(mask, tri, ds)
     same = (d[:, 1:].sign() * d[:, :-1].sign() == 1)
     return same.to(ds.dtype) * ds

@@ -51,7 +51,8 @@ __device__ __forceinline__ double warp_excl_scan(const float (&v)[C], double (&e
     double t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  double base = incl - run;
+  double base = __shfl_up_sync(0xffffffffu, incl, 1);  // previous lanes' total (not `incl - run`: cancels)
+  if (lane == 0) base = 0.0;
 #pragma unroll
   for (int j = 0; j < C; ++j) excl[j] += base;
   return __shfl_sync(0xffffffffu, incl, 31);

@@ -41,6 +41,14 @@ __device__ __forceinline__ T warp_incl_scan(T v, int lane) {
   return v;
 }
 
+// exclusive prefix from the inclusive one: the previous lane's value (never `incl - self`, which cancels
+// and loses the low bits of a small prefix next to a large element)
+template <typename T>
+__device__ __forceinline__ T excl_of(T incl, int lane) {
+  T prev = __shfl_up_sync(0xffffffffu, incl, 1);
+  return lane ? prev : (T)0;
+}
+
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
 // LaplaceDensity.density_func with an explicit beta (density.py:21-26)
@@ -132,7 +140,7 @@ __device__ __forceinline__ float error_bound(const float* ssdf, const float* sdi
     }
     acc_t incl_i = warp_incl_scan<acc_t>((acc_t)sfe, lane);
     acc_t incl_e = warp_incl_scan<acc_t>((acc_t)es, lane);
-    float integral = (float)(carry_i + incl_i - (acc_t)sfe);  // exclusive prefix, rounded
+    float integral = (float)(carry_i + excl_of(incl_i, lane));  // exclusive prefix, rounded
     float eint = (float)(carry_e + incl_e);                   // inclusive prefix, rounded
     if (valid) {
       float bo = (fminf(t_exp<X>(eint), 1.0e6f) - 1.0f) * t_exp<X>(-integral);
@@ -269,7 +277,7 @@ sampler_resample_kernel(svs_sampler_cfg c, int64_t R, int n, int n_u, int n_u_pa
         }
       }
       acc_t incl_f = warp_incl_scan<acc_t>((acc_t)fe, lane);
-      float T = t_exp<X>(-(float)(carry_f + incl_f - (acc_t)fe));
+      float T = t_exp<X>(-(float)(carry_f + excl_of(incl_f, lane)));
       float p = 0.f;
       if (cont) {
         acc_t incl_e = warp_incl_scan<acc_t>((acc_t)es, lane);
@@ -302,7 +310,7 @@ sampler_resample_kernel(svs_sampler_cfg c, int64_t R, int n, int n_u, int n_u_pa
       int i = base + lane;
       float p = (i < n - 1) ? (scdf[i] / total) : 0.f;
       acc_t incl = warp_incl_scan<acc_t>((acc_t)p, lane);
-      float cexcl = (float)(carry_c + incl - (acc_t)p);
+      float cexcl = (float)(carry_c + excl_of(incl, lane));
       __syncwarp();
       if (i < n) scdf[i] = cexcl;
       carry_c += __shfl_sync(0xffffffffu, incl, 31);

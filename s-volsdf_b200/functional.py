@@ -83,6 +83,8 @@ def sdf_forward_nograd(net, x, want_y, want_sdf):
     ws = _f32(max(1, int(L.load().svs_sdf_ws_floats(net.desc, P, 0))), device=dev)
     y = _f32(P, net.ldy, device=dev) if want_y else None
     sdf = _f32(P, 1, device=dev) if want_sdf else None
+    if P == 0:
+        return y, sdf
     L.call('svs_sdf_forward', net.desc, ptr(wbuf), ptr(x), P, ptr(y), ptr(sdf), ptr(ws), net.engine, L.stream())
     return y, sdf
 
@@ -94,11 +96,10 @@ class SdfOutputsFn(torch.autograd.Function):
     and the double-backward through the analytic gradient."""
 
     @staticmethod
-    def forward(ctx, net, x, clamp, want_grad, *params):
+    def forward(ctx, net, x, clamp, want_grad, train, *params):
         x = x.detach().contiguous().float()
         P = x.shape[0]
         dev = x.device
-        train = net.needs_grad()
         wbuf = net.prepare(dev)
         lib = L.load()
         y = _f32(P, net.ldy, device=dev)
@@ -128,11 +129,11 @@ class SdfOutputsFn(torch.autograd.Function):
         L.call('svs_sdf_outputs_backward', net.desc, ptr(wbuf), ptr(x), P, 1 if ctx.clamp else 0, ptr(saved), ptr(y),
                ptr(dy), ptr(d_sdf), ptr(d_grad), ptr(dwbuf), ptr(ws), net.engine, L.stream())
         grads = net.param_grads(wbuf, dwbuf)
-        return (None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None) + tuple(grads)
 
 
 def sdf_outputs(net, x, clamp=True, want_grad=True):
-    return SdfOutputsFn.apply(net, x, clamp, want_grad, *net.flat_params())
+    return SdfOutputsFn.apply(net, x, clamp, want_grad, net.needs_grad(), *net.flat_params())
 
 
 class RenderFn(torch.autograd.Function):
@@ -140,7 +141,7 @@ class RenderFn(torch.autograd.Function):
     `feat_col`; its gradient comes back with the same full width so no slicing copies are needed."""
 
     @staticmethod
-    def forward(ctx, net, points, normals, view_dirs, feat, feat_col, *params):
+    def forward(ctx, net, points, normals, view_dirs, feat, feat_col, train, *params):
         dev = view_dirs.device
         P = view_dirs.shape[0]
         view_dirs = view_dirs.detach().contiguous().float()
@@ -153,7 +154,6 @@ class RenderFn(torch.autograd.Function):
         ld_feat = f.stride(0)
         fptr = f.data_ptr() + 4 * feat_col
         lib = L.load()
-        train = net.needs_grad() or (torch.is_grad_enabled() and (feat.requires_grad or (idr and normals.requires_grad)))
         wbuf = net.prepare(dev)
         saved = _f32(max(1, int(lib.svs_render_saved_floats(net.desc, P))), device=dev)
         rgb = _f32(P, net.desc.out_dim[net.desc.n_layers - 1], device=dev)
@@ -178,11 +178,13 @@ class RenderFn(torch.autograd.Function):
                ptr(d_normals), d_feat.data_ptr() + 4 * ctx.feat_col, d_feat.stride(0), ptr(dwbuf), ptr(ws),
                net.engine, L.stream())
         grads = net.param_grads(wbuf, dwbuf)
-        return (None, None, d_normals, None, d_feat, None) + tuple(grads)
+        return (None, None, d_normals, None, d_feat, None, None) + tuple(grads)
 
 
 def render(net, points, normals, view_dirs, feat, feat_col=0):
-    return RenderFn.apply(net, points, normals, view_dirs, feat, feat_col, *net.flat_params())
+    train = net.needs_grad() or (torch.is_grad_enabled() and (
+        feat.requires_grad or (normals is not None and normals.requires_grad)))
+    return RenderFn.apply(net, points, normals, view_dirs, feat, feat_col, train, *net.flat_params())
 
 
 class CompositeFn(torch.autograd.Function):

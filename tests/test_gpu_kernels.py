@@ -285,7 +285,7 @@ def test_depth2pts_outside(bmvs):
     mb, _ = bmvs
     inp = S.make_input('bmvs', 128)
     rd, cl = O.get_camera_params(inp['uv'], inp['pose'], inp['intrinsics'])
-    depth = torch.rand(128, 32, generator=torch.Generator().manual_seed(2))
+    depth = torch.rand(128, 32, generator=torch.Generator().manual_seed(2)) / 3.0   # 1/r with r >= R_s = 3
     o = cl.unsqueeze(1).repeat(128, 32, 1)
     dd = rd[0].unsqueeze(1).repeat(1, 32, 1)
     pts, dreal = O.depth2pts_outside(o, dd, depth, 3.0)
