@@ -73,6 +73,13 @@ const char* svs_last_error(void);
 int svs_abi_version(void);
 /* 1 when the library was built with the tcgen05 (sm_100a) engine */
 int svs_has_engine(int engine);
+/* number of kernels this library has launched so far (bench.py's gpu_launches) */
+int64_t svs_launch_count(void);
+/* Optional per-kernel profiler: while enabled every launch is bracketed by CUDA events on its stream.
+ * svs_prof_collect synchronises them and writes "name\tlaunches\ttotal_ms\tflops\tbytes\n" per kernel name
+ * (flops/bytes = ALGORITHMIC work summed over the launches) into buf; returns the length or <0. */
+int svs_prof_enable(int on);
+int64_t svs_prof_collect(char* buf, int64_t cap);
 
 /* ---------------------------------------------------------------------------------------------------
  * Weights.  Replaces the weight_norm pre-forward hook (network.py:64-65: W = g*v/|v| recomputed on every

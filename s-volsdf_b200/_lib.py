@@ -49,6 +49,9 @@ SIGNATURES = {
     'svs_last_error': (C.c_char_p, []),
     'svs_abi_version': (C.c_int, []),
     'svs_has_engine': (C.c_int, [C.c_int]),
+    'svs_launch_count': (_I64, []),
+    'svs_prof_enable': (C.c_int, [C.c_int]),
+    'svs_prof_collect': (_I64, [C.c_char_p, _I64]),
     'svs_mlp_wbuf_floats': (_I64, [_DESC]),
     'svs_mlp_prepare': (C.c_int, [_DESC, _PAR, _P, C.c_int, _P]),
     'svs_mlp_param_grads': (C.c_int, [_DESC, _PAR, _P, _P, _PAR, _P]),
@@ -132,6 +135,27 @@ def make_desc(kind, in_dims, out_dims, d_in=3, n_freqs=0, skip_layer=-1, render_
         d.in_dim[l], d.out_dim[l] = i, o
     d.sphere_radius, d.sphere_scale = sphere_radius, sphere_scale
     return d
+
+
+def launch_count():
+    return int(load().svs_launch_count())
+
+
+def prof_enable(on):
+    load().svs_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """-> {kernel name: {'launches', 'ms', 'flops', 'bytes'}} for everything recorded since the last call."""
+    buf = C.create_string_buffer(1 << 16)
+    n = load().svs_prof_collect(buf, len(buf))
+    if n < 0:
+        raise SvsError('svs_prof_collect failed: %s' % load().svs_last_error().decode())
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, flops, nbytes = line.split('\t')
+        out[name] = {'launches': int(cnt), 'ms': float(ms), 'flops': float(flops), 'bytes': float(nbytes)}
+    return out
 
 
 def make_params(gs, vs, bs):

@@ -369,6 +369,7 @@ extern "C" int svs_composite_forward(const float* z, const float* sdf, const flo
   SVS_CHECK_ARG(!rgb_values || rgb, "svs_composite_forward: rgb required for rgb_values");
   if (R == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps("composite_fwd", 0.0, (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (normal_map ? 3 : 0)) + 32), st);
   DISPATCH_C(S, (composite_fwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
                     z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
                     rgb_values, depth_values, normal_map, bg_trans)));
@@ -389,6 +390,8 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   SVS_CHECK_ARG(!d_rgb || rgb, "svs_composite_backward: rgb required for d_rgb");
   if (R == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps("composite_bwd", 0.0,
+               (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (d_weights ? 1 : 0) + (d_rgb ? 3 : 0)) + 32), st);
   DISPATCH_C(S, (composite_bwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
                     z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                     d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));

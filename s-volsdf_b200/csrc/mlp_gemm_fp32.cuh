@@ -297,6 +297,8 @@ template <bool TRANS_B, int EPI>
 static int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 0 || a.N <= 0) return SVS_OK;
   dim3 grid((unsigned)cdiv(a.M, GBM), (unsigned)cdiv(a.N, GBN));
+  ProfScope ps(TRANS_B ? "mlp_gemm_nt_fp32" : "mlp_gemm_nn_fp32", 2.0 * a.M * a.N * a.K,
+               4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N), st);
   gemm_kernel<TRANS_B, EPI><<<grid, 256, 0, st>>>(a);
   SVS_LAUNCH_OK();
   return SVS_OK;
@@ -312,6 +314,7 @@ static int launch_gemm_tn(const float* A1, int lda1, const float* A2, int lda2, 
   if (rows < 256) rows = 256;
   int chunks = (int)cdiv(M, rows);
   dim3 grid((unsigned)tiles, (unsigned)chunks);
+  ProfScope ps("mlp_gemm_tn_fp32", 2.0 * M * N * K, 4.0 * ((double)M * N + (double)M * K + (double)N * K), st);
   gemm_tn_kernel<<<grid, 256, 0, st>>>(A1, lda1, A2, lda2, dW, ldw, (int)M, N, K, tiles_k, (int)rows);
   SVS_LAUNCH_OK();
   return SVS_OK;

@@ -434,6 +434,7 @@ extern "C" int svs_sampler_init(const svs_sampler_cfg* c, int64_t R, int32_t n, 
   SVS_CHECK_ARG(c->far >= 0.f || far_ray, "svs_sampler_init: far_ray required when cfg.far < 0");
   if (R == 0) return SVS_OK;
   size_t smem = (size_t)kSampWarps * n * sizeof(float);
+  ProfScope ps("sampler_init", 0.0, (double)R * (4.0 * n * (t_rand ? 2 : 1) + 4), (cudaStream_t)stream);
   sampler_init_kernel<<<samp_grid(R), kSampWarps * 32, smem, (cudaStream_t)stream>>>(*c, R, n, t_lin, t_rand,
                                                                                     far_ray, z, beta);
   SVS_LAUNCH_OK();
@@ -451,6 +452,7 @@ extern "C" int svs_sampler_bound(const svs_sampler_cfg* c, int64_t R, int32_t n,
   if (R == 0) return SVS_OK;
   size_t smem = (size_t)kSampWarps * 4 * n * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps("sampler_bound", 0.0, (double)R * (4.0 * n * (samples_idx ? 4 : 3) + 8), st);
   if (c->exact) {
     SVS_TRY(set_smem(sampler_bound_kernel<true>, smem));
     sampler_bound_kernel<true><<<samp_grid(R), kSampWarps * 32, smem, st>>>(
@@ -475,6 +477,8 @@ extern "C" int svs_sampler_resample(const svs_sampler_cfg* c, int64_t R, int32_t
   int n_u_pad = next_pow2(n_u < 32 ? 32 : n_u);
   size_t smem = (size_t)kSampWarps * (4 * n + 2 * n_u_pad) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps("sampler_resample", 0.0,
+               (double)R * (8.0 * n + 4 + 4.0 * n_u * (u_per_ray ? 2 : 1) + (cont ? 8.0 * (n + n_u) : 0.0)), st);
   if (c->exact) {
     SVS_TRY(set_smem(sampler_resample_kernel<true>, smem));
     sampler_resample_kernel<true><<<samp_grid(R), kSampWarps * 32, smem, st>>>(
@@ -501,6 +505,7 @@ extern "C" int svs_sampler_finalize(const svs_sampler_cfg* c, int64_t R, int32_t
   if (R == 0) return SVS_OK;
   int m_pad = next_pow2(m < 64 ? 64 : m);
   size_t smem = (size_t)kSampWarps * 2 * m_pad * sizeof(float);
+  ProfScope ps("sampler_finalize", 0.0, (double)R * (4.0 * (n_samples + n_extra) + 4.0 * m + 16), (cudaStream_t)stream);
   sampler_finalize_kernel<<<samp_grid(R), kSampWarps * 32, smem, (cudaStream_t)stream>>>(
       *c, R, n, n_samples, m_pad, z, samples, extra_idx, n_extra, far_ray, eik_idx, z_final, z_eik);
   SVS_LAUNCH_OK();

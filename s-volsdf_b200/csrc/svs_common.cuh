@@ -28,7 +28,27 @@ void set_error(const char* fmt, ...);
     }                                                                                      \
   } while (0)
 
-#define SVS_LAUNCH_OK() SVS_CUDA_OK(cudaGetLastError())
+void count_launch();
+bool prof_enabled();
+int prof_begin(const char* name, double flops, double bytes, cudaStream_t st);
+void prof_end(int id, cudaStream_t st);
+
+// RAII profiling range around one kernel launch (no-op unless svs_prof_enable(1))
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  ProfScope(const char* name, double flops, double bytes, cudaStream_t s)
+      : id(prof_enabled() ? prof_begin(name, flops, bytes, s) : -1), st(s) {}
+  ~ProfScope() {
+    if (id >= 0) prof_end(id, st);
+  }
+};
+
+#define SVS_LAUNCH_OK()                \
+  do {                                 \
+    svs::count_launch();               \
+    SVS_CUDA_OK(cudaGetLastError());   \
+  } while (0)
 
 #define SVS_TRY(expr)          \
   do {                         \

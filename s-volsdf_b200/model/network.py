@@ -207,7 +207,7 @@ class VolSDFNetwork(nn.Module):
         dev = uv.device
         ray_dirs, cam_loc, depth_scale = self._rays(uv, pose, intrinsics)
         R = ray_dirs.shape[0]
-        rng = RefRng(dev)
+        rng = self.rng_source if getattr(self, 'rng_source', None) is not None else RefRng(dev)
         self.last_rng = rng
         z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, fast=fast, iter_step=iter_step,
                                                             _rng=rng)

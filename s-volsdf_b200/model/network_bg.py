@@ -49,7 +49,7 @@ class VolSDFNetworkBG(nn.Module):
         dev = uv.device
         ray_dirs, cam_loc, depth_scale = F.raygen(uv[0], pose[0], intrinsics[0])
         R = ray_dirs.shape[0]
-        rng = RefRng(dev)
+        rng = self.rng_source if getattr(self, 'rng_source', None) is not None else RefRng(dev)
         self.last_rng = rng
         (z_all, z_vals_bg), z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, fast=fast, _rng=rng)
         self.last_z = ((z_all, z_vals_bg), z_samples_eik)

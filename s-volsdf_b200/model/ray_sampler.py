@@ -39,6 +39,60 @@ class RefRng(object):
         return self._up(torch.empty(shape, pin_memory=True).uniform_(lo, hi))
 
 
+class RecordedRng(RefRng):
+    """Replays draws that were made (in the reference's order) and uploaded ahead of time: used when the
+    caller wants the step's inputs resident in HBM before it starts (bench.py's device-timed `value`)."""
+
+    def __init__(self, device, tape):
+        super().__init__(device)
+        self.tape = list(tape)
+        self.pos = 0
+
+    def _next(self):
+        t = self.tape[self.pos]
+        self.pos += 1
+        return t
+
+    def rand(self, *shape):
+        return self._next()
+
+    def randperm(self, n):
+        return self._next()
+
+    def randint(self, high, shape):
+        return self._next()
+
+    def uniform(self, shape, lo, hi):
+        return self._next()
+
+
+class TapeRng(object):
+    """Wraps a RefRng-like source and records the device tensors it hands out (to build RecordedRng tapes)."""
+
+    def __init__(self, inner):
+        self.inner, self.tape = inner, []
+
+    @property
+    def h2d_bytes(self):
+        return self.inner.h2d_bytes
+
+    def _rec(self, t):
+        self.tape.append(t)
+        return t
+
+    def rand(self, *shape):
+        return self._rec(self.inner.rand(*shape))
+
+    def randperm(self, n):
+        return self._rec(self.inner.randperm(n))
+
+    def randint(self, high, shape):
+        return self._rec(self.inner.randint(high, shape))
+
+    def uniform(self, shape, lo, hi):
+        return self._rec(self.inner.uniform(shape, lo, hi))
+
+
 _const_cache = {}
 
 
