@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--rays', type=int, default=1024, help='rays per GPU per step')
-    ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'bf16'])
+    ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc'])
     ap.add_argument('--cpu-rays', type=int, default=128, help='rays per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -206,8 +206,8 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     L.load()
     engine = L.ENGINE_FP32
-    if args.engine == 'bf16' or (args.engine == 'auto' and L.load().svs_has_engine(L.ENGINE_BF16)):
-        engine = L.ENGINE_BF16
+    if args.engine == 'tc' or (args.engine == 'auto' and L.load().svs_has_engine(L.ENGINE_TC)):
+        engine = L.ENGINE_TC
     K, W, R = args.steps, max(args.warmup, 3), args.rays
     Rg = R * world
 
@@ -352,12 +352,12 @@ def run_ours(args):
     line = {
         'metric': 'rays/sec (fwd+bwd train step)', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if engine == L.ENGINE_BF16 else 'f32', 'data': 'synthetic',
+        'dtype': 'f16' if engine == L.ENGINE_TC else 'f32', 'data': 'synthetic',
         'config': {'workload': 'DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
                                'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam', 'rays_per_gpu': R,
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~3 GB of saved activations) exceeds the 126 MB L2; no explicit flush',
-                   'engine': 'bf16 tcgen05' if engine == L.ENGINE_BF16 else 'fp32 SIMT (parity mode)'},
+                   'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)'},
         'e2e': {'value': Rg / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,

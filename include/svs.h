@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define SVS_MAX_LAYERS 12
-#define SVS_ABI_VERSION 1
+#define SVS_ABI_VERSION 2
 
 typedef enum {
   SVS_OK = 0,
@@ -38,7 +38,8 @@ typedef enum {
 /* arithmetic engine of the MLP kernels */
 typedef enum {
   SVS_ENGINE_FP32 = 0, /* fp32 SIMT FFMA tiles: parity mode (rgb/depth <= 1e-3 vs the reference) */
-  SVS_ENGINE_BF16 = 1  /* tcgen05.mma kind::f16 (bf16 operands, fp32 TMEM accumulators) */
+  SVS_ENGINE_TC = 1    /* tcgen05.mma kind::f16: fp16 operands (10-bit mantissa, TF32-class), fp32 TMEM accumulators;
+                          activations stay in shared memory across the layers of a chain (mlp_tc.cuh) */
 } svs_engine;
 
 typedef enum { SVS_NET_SDF = 0, SVS_NET_RENDER = 1 } svs_net_kind;
@@ -71,7 +72,7 @@ typedef struct {
 
 const char* svs_last_error(void);
 int svs_abi_version(void);
-/* 1 when the library was built with the tcgen05 (sm_100a) engine */
+/* 1 when the library provides the engine (both are always built for sm_100a) */
 int svs_has_engine(int engine);
 /* number of kernels this library has launched so far (bench.py's gpu_launches) */
 int64_t svs_launch_count(void);
@@ -86,7 +87,7 @@ int64_t svs_prof_collect(char* buf, int64_t cap);
  * call) and its autograd backward.  `wbuf` holds the effective weights of all layers in the layout the
  * kernels consume (svs_mlp_wbuf_floats elements); the same layout is used for the gradient accumulator.
  * ------------------------------------------------------------------------------------------------- */
-int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d);
+int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d, int engine);
 int svs_mlp_prepare(const svs_mlp_desc* d, const svs_mlp_params* p, float* wbuf, int engine, void* stream);
 /* dwbuf (dL/dW_eff, dL/db in wbuf layout) -> dL/dg, dL/dv, dL/db written (not accumulated) to `grads` */
 int svs_mlp_param_grads(const svs_mlp_desc* d, const svs_mlp_params* p, const float* wbuf,
@@ -106,8 +107,8 @@ int svs_mlp_param_grads(const svs_mlp_desc* d, const svs_mlp_params* p, const fl
  * `ws` is scratch of svs_sdf_ws_floats(d, P, training) elements.  ldy = svs_sdf_ldy(d).
  * ------------------------------------------------------------------------------------------------- */
 int32_t svs_sdf_ldy(const svs_mlp_desc* d);
-int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad);
-int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P);
+int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad, int engine);
+int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P, int engine);
 int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, float* y,
                     float* sdf, float* ws, int engine, void* stream);
 int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
@@ -116,7 +117,7 @@ int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const floa
 int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
                              const float* saved, const float* y, const float* dy, const float* d_sdf,
                              const float* d_grad, float* dwbuf, float* ws, int engine, void* stream);
-int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P);
+int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P, int engine);
 
 /* Positional encoding on its own (embedder.py:10-36 `Embedder.embed`): x (P,d_in) -> out (P, d_in*(1+2*n_freqs)). */
 int svs_embed(const float* x, int64_t P, int32_t d_in, int32_t n_freqs, float* out, void* stream);
@@ -129,8 +130,8 @@ int svs_embed(const float* x, int64_t P, int32_t d_in, int32_t n_freqs, float* o
  *   accumulates weight gradients into dwbuf.  points / view dirs carry no gradient on the hot path
  *   (the sampler runs under no_grad, ray_sampler.py:88-89).
  * ------------------------------------------------------------------------------------------------- */
-int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P);
-int64_t svs_render_ws_floats(const svs_mlp_desc* d, int64_t P);
+int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P, int engine);
+int64_t svs_render_ws_floats(const svs_mlp_desc* d, int64_t P, int engine);
 int svs_render_forward(const svs_mlp_desc* d, const float* wbuf, const float* points, const float* view_dirs,
                        const float* normals, const float* feat, int32_t ld_feat, int64_t P, float* rgb,
                        float* saved, int engine, void* stream);

@@ -11,7 +11,7 @@ import os
 import torch
 
 SVS_MAX_LAYERS = 12
-ENGINE_FP32, ENGINE_BF16 = 0, 1
+ENGINE_FP32, ENGINE_TC = 0, 1
 NET_SDF, NET_RENDER = 0, 1
 RENDER_IDR, RENDER_NERF = 0, 1
 COMP_ABS_DENSITY, COMP_REVERSED, COMP_ZMAX_TAIL = 1, 2, 4
@@ -52,19 +52,19 @@ SIGNATURES = {
     'svs_launch_count': (_I64, []),
     'svs_prof_enable': (C.c_int, [C.c_int]),
     'svs_prof_collect': (_I64, [C.c_char_p, _I64]),
-    'svs_mlp_wbuf_floats': (_I64, [_DESC]),
+    'svs_mlp_wbuf_floats': (_I64, [_DESC, C.c_int]),
     'svs_mlp_prepare': (C.c_int, [_DESC, _PAR, _P, C.c_int, _P]),
     'svs_mlp_param_grads': (C.c_int, [_DESC, _PAR, _P, _P, _PAR, _P]),
     'svs_sdf_ldy': (_I32, [_DESC]),
-    'svs_sdf_ws_floats': (_I64, [_DESC, _I64, C.c_int]),
-    'svs_sdf_saved_floats': (_I64, [_DESC, _I64]),
-    'svs_sdf_bwd_ws_floats': (_I64, [_DESC, _I64]),
+    'svs_sdf_ws_floats': (_I64, [_DESC, _I64, C.c_int, C.c_int]),
+    'svs_sdf_saved_floats': (_I64, [_DESC, _I64, C.c_int]),
+    'svs_sdf_bwd_ws_floats': (_I64, [_DESC, _I64, C.c_int]),
     'svs_sdf_forward': (C.c_int, [_DESC, _P, _P, _I64, _P, _P, _P, C.c_int, _P]),
     'svs_sdf_outputs_forward': (C.c_int, [_DESC, _P, _P, _I64, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
     'svs_sdf_outputs_backward': (C.c_int, [_DESC, _P, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     'svs_embed': (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
-    'svs_render_saved_floats': (_I64, [_DESC, _I64]),
-    'svs_render_ws_floats': (_I64, [_DESC, _I64]),
+    'svs_render_saved_floats': (_I64, [_DESC, _I64, C.c_int]),
+    'svs_render_ws_floats': (_I64, [_DESC, _I64, C.c_int]),
     'svs_render_forward': (C.c_int, [_DESC, _P, _P, _P, _P, _P, _I32, _I64, _P, _P, C.c_int, _P]),
     'svs_render_backward': (C.c_int, [_DESC, _P, _I64, _P, _P, _P, _P, _P, _I32, _P, _P, C.c_int, _P]),
     'svs_raygen': (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),

@@ -51,11 +51,7 @@ void prof_end(int id, cudaStream_t st) {
 extern "C" const char* svs_last_error(void) { return svs::g_err; }
 extern "C" int svs_abi_version(void) { return SVS_ABI_VERSION; }
 extern "C" int svs_has_engine(int engine) {
-#ifdef SVS_WITH_TCGEN05
-  return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_BF16;
-#else
-  return engine == SVS_ENGINE_FP32;
-#endif
+  return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC;
 }
 
 extern "C" int64_t svs_launch_count(void) { return svs::g_launches; }

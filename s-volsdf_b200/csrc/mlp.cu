@@ -380,15 +380,20 @@ static inline unsigned blocks_for(int64_t n) { return (unsigned)cdiv(n, 256); }
 
 }  // namespace svs
 
+#include "mlp_tc_chains.cuh"
+
 using namespace svs;
 
 // ====================================================================================================
 // C ABI
 // ====================================================================================================
 
-extern "C" int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d) {
+static bool engine_ok(int engine) { return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC; }
+
+extern "C" int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) return tc::wbuf_floats_tc(d, lo);
   return lo.total;
 }
 
@@ -396,7 +401,7 @@ extern "C" int svs_mlp_prepare(const svs_mlp_desc* d, const svs_mlp_params* p, f
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
   SVS_CHECK_ARG(p && wbuf, "svs_mlp_prepare: null pointer");
-  SVS_CHECK_ARG(engine == SVS_ENGINE_FP32, "svs_mlp_prepare: engine %d not built", engine);
+  SVS_CHECK_ARG(engine_ok(engine), "svs_mlp_prepare: engine %d not built", engine);
   for (int l = 0; l < lo.L; ++l) {
     SVS_CHECK_ARG(p->v[l] && p->b[l], "svs_mlp_prepare: layer %d missing weight/bias", l);
     SVS_CHECK_ARG((d->weight_norm != 0) == (p->g[l] != nullptr), "svs_mlp_prepare: layer %d weight_g mismatch", l);
@@ -405,6 +410,7 @@ extern "C" int svs_mlp_prepare(const svs_mlp_desc* d, const svs_mlp_params* p, f
   fill_pack(lo, p, nullptr, &a);
   pack_weights_kernel<<<(unsigned)cdiv(a.row0[lo.L], 4), 128, 0, (cudaStream_t)stream>>>(a, wbuf);
   SVS_LAUNCH_OK();
+  if (engine == SVS_ENGINE_TC) SVS_TRY(tc::pack_images(d, lo, wbuf, (cudaStream_t)stream));
   return SVS_OK;
 }
 
@@ -444,29 +450,41 @@ extern "C" int32_t svs_sdf_ldy(const svs_mlp_desc* d) {
   return lo.ldy;
 }
 
-extern "C" int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P) {
+extern "C" int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) {
+    tc::SdfSaved sv;
+    tc::map_sdf_saved(lo, P, nullptr, &sv);
+    return sv.bytes / 4;
+  }
   return P * ((int64_t)lo.ld0 + 2 * (int64_t)(lo.L - 1) * lo.H);
 }
 
-extern "C" int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad) {
+extern "C" int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
-  if (with_grad) return svs_sdf_saved_floats(d, P) + P * 2 * (int64_t)lo.ld0;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) return with_grad ? svs_sdf_saved_floats(d, P, engine) : 4;
+  if (with_grad) return svs_sdf_saved_floats(d, P, engine) + P * 2 * (int64_t)lo.ld0;
   return P * ((int64_t)lo.ld0 + 2 * (int64_t)lo.H + lo.ldy);
 }
 
-extern "C" int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P) {
+extern "C" int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) {
+    tc::SdfBwdWs bw;
+    tc::map_sdf_bwd(lo, P, nullptr, &bw);
+    return bw.bytes / 4;
+  }
   return P * ((int64_t)lo.ld0 + (int64_t)(4 + lo.L - 1) * lo.H + lo.ldy);
 }
 
 static int check_sdf(const svs_mlp_desc* d, const Layout& lo, int engine) {
   SVS_CHECK_ARG(d->kind == SVS_NET_SDF, "descriptor is not an SDF net");
-  SVS_CHECK_ARG(engine == SVS_ENGINE_FP32, "engine %d not built", engine);
-  for (int l = 1; l < lo.L; ++l) SVS_CHECK_ARG(lo.ldi[l] == lo.H, "hidden widths must be uniform (layer %d)", l);
+  SVS_CHECK_ARG(engine_ok(engine), "engine %d not built", engine);
+  if (engine == SVS_ENGINE_FP32)
+    for (int l = 1; l < lo.L; ++l) SVS_CHECK_ARG(lo.ldi[l] == lo.H, "hidden widths must be uniform (layer %d)", l);
   return SVS_OK;
 }
 
@@ -478,6 +496,7 @@ extern "C" int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const f
   SVS_CHECK_ARG(wbuf && x && ws && (y || sdf) && P >= 0, "svs_sdf_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == SVS_ENGINE_TC) return tc::sdf_forward(d, lo, wbuf, x, P, y, sdf, st);
   float* A0 = ws;
   float* B[2] = {A0 + P * lo.ld0, A0 + P * lo.ld0 + P * lo.H};
   float* Y = y ? y : (B[1] + P * lo.H);
@@ -540,13 +559,25 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
   SVS_CHECK_ARG(wbuf && x && y && ws && P >= 0, "svs_sdf_outputs_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == SVS_ENGINE_TC) {
+    if (!grad && !saved) {
+      SVS_TRY(tc::sdf_forward(d, lo, wbuf, x, P, y, nullptr, st));
+      if (sdf) {
+        sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, clamp ? d->sphere_radius : 0.f,
+                                                        d->sphere_scale, sdf);
+        SVS_LAUNCH_OK();
+      }
+      return SVS_OK;
+    }
+    return tc::sdf_outputs_forward(d, lo, wbuf, x, P, clamp, y, sdf, grad, saved ? (void*)saved : (void*)ws, st);
+  }
   SdfBuffers b;
   float* scratch = ws;
   if (saved) {
     map_saved(lo, P, saved, &b);
   } else {
     map_saved(lo, P, ws, &b);
-    scratch = ws + svs_sdf_saved_floats(d, P);
+    scratch = ws + svs_sdf_saved_floats(d, P, SVS_ENGINE_FP32);
   }
   float* P0 = scratch;
   float* E = scratch + P * lo.ld0;
@@ -627,6 +658,8 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
   SVS_CHECK_ARG(wbuf && x && saved && y && dwbuf && ws && P >= 0, "svs_sdf_outputs_backward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == SVS_ENGINE_TC)
+    return tc::sdf_outputs_backward(d, lo, wbuf, x, P, clamp, saved, y, dy, d_sdf, d_grad, dwbuf, ws, st);
   const int L = lo.L;
   SdfBuffers b;
   map_saved(lo, P, const_cast<float*>(saved), &b);
@@ -724,7 +757,7 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
 
 static int check_render(const svs_mlp_desc* d, const Layout& lo, int engine, int* pe_v, int* F) {
   SVS_CHECK_ARG(d->kind == SVS_NET_RENDER, "descriptor is not a rendering net");
-  SVS_CHECK_ARG(engine == SVS_ENGINE_FP32, "engine %d not built", engine);
+  SVS_CHECK_ARG(engine_ok(engine), "engine %d not built", engine);
   *pe_v = 3 * (1 + 2 * d->n_freqs);
   int fixed = (d->render_mode == SVS_RENDER_IDR) ? 6 + *pe_v : *pe_v;
   *F = lo.in[0] - fixed;
@@ -733,15 +766,27 @@ static int check_render(const svs_mlp_desc* d, const Layout& lo, int engine, int
   return SVS_OK;
 }
 
-extern "C" int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P) {
+extern "C" int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) {
+    tc::WImages wi;
+    if (tc::make_wimages(d, lo, &wi, nullptr, nullptr) != SVS_OK) return -1;
+    tc::RenderSaved sv;
+    tc::map_render_saved(lo, wi, P, nullptr, &sv);
+    return sv.bytes / 4;
+  }
   return P * ((int64_t)lo.ld0 + (int64_t)(lo.L - 1) * lo.H);
 }
 
-extern "C" int64_t svs_render_ws_floats(const svs_mlp_desc* d, int64_t P) {
+extern "C" int64_t svs_render_ws_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
-  if (make_layout(d, &lo) != SVS_OK) return -1;
+  if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
+  if (engine == SVS_ENGINE_TC) {
+    tc::RenderWs rw;
+    tc::map_render_ws(lo, P, nullptr, &rw);
+    return rw.bytes / 4;
+  }
   return P * ((int64_t)lo.ld0 + 2 * (int64_t)lo.H + 4);
 }
 
@@ -758,6 +803,8 @@ extern "C" int svs_render_forward(const svs_mlp_desc* d, const float* wbuf, cons
   SVS_CHECK_ARG(ld_feat >= F, "svs_render_forward: ld_feat %d < feature width %d", ld_feat, F);
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == SVS_ENGINE_TC)
+    return tc::render_forward(d, lo, wbuf, points, view_dirs, normals, feat, ld_feat, P, rgb, saved, st);
   const int L = lo.L;
   float* RIN = saved;
   float* Bv[SVS_MAX_LAYERS];
@@ -803,6 +850,8 @@ extern "C" int svs_render_backward(const svs_mlp_desc* d, const float* wbuf, int
   SVS_CHECK_ARG(wbuf && saved && rgb && d_rgb && dwbuf && ws && P >= 0, "svs_render_backward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine == SVS_ENGINE_TC)
+    return tc::render_backward(d, lo, wbuf, P, saved, rgb, d_rgb, d_normals, d_feat, ld_dfeat, dwbuf, ws, st);
   const int L = lo.L;
   const float* RIN = saved;
   const float* Bv[SVS_MAX_LAYERS];

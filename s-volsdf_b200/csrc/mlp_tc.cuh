@@ -1,0 +1,747 @@
+// SVS_ENGINE_TC: the MLP chains of the VolSDF hot path on tcgen05 tensor cores (sm_100a).
+//
+// One persistent CTA per SM walks 128-point tiles.  For every tile a *chain* of steps runs with the activations
+// resident in shared memory: step = [tcgen05.mma: acc(TMEM, fp32) = A(smem, fp16) x W^T(smem, fp16)] followed by
+// an element-wise epilogue (TMEM -> registers -> fp16 -> the same smem tile, in place) that produces the A operand
+// of the next step.  Layer weights are streamed from L2 as pre-packed SWIZZLE_128B images by 1-D bulk copies
+// (UBLKCP) through a 2-slot ring; the activations a later pass needs (backward, weight gradients) are saved as
+// tile images with bulk stores straight from the smem tile, and read back the same way ("aux" ring).
+//
+// Warp roles (640 threads): warp 0 weight producer, warp 1 MMA issuer (one elected lane), warp 2 aux producer +
+// TMEM allocation, warps 4..19 epilogue (TMEM lane quarter = warp % 4, 16-column quarter of a block = (warp-4)/4).
+// MMA and epilogue overlap at 64-column granularity: as soon as all epilogue warps have rewritten block c of the
+// tile, the MMAs of the NEXT step that consume block c are issued into the other half of the 512 TMEM columns.
+//
+// Chains (math: SURVEY.md Appendix F; reference: volsdf/model/network.py:71-123,170-190 and its autograd graph):
+//   sdf forward        PE -> 8 x softplus layer -> sdf (no-grad) | y = [sdf, features] (+ saved h_1..h_8)
+//   sdf reverse sweep  U_7 = s(h_8) * W_8[0,:] -> U_{l-1} = s(h_l) * (U_l W_l) -> g = J_PE^T (U_0 W_0 + E), sphere clamp
+//   render forward     [feat | x, PE(d), n] -> 4 x relu layer -> sigmoid
+//   render backward    dz_4 = d_rgb rgb (1-rgb) -> dz_{l-1} = relu'(h_l) * (dz_l W_l) -> d_feat, d_normals
+//   sdf tangent sweep  q_0 = J_PE (w d_grad) -> r_l = q_l W_l^T ; zeta_l = beta (1-s) U_l r_l ; q_{l+1} = s r_l
+//   sdf backward       dz_8 = dy -> dz_{l-1} = s(h_l) * (dz_l W_l) + zeta_{l-1}
+// Weight gradients dW_l = sum_p X[p,:]^T Y[p,:] are a separate kernel (tc_dw_kernel) that reads the saved images as
+// MN-major operands and keeps the 256x256 fp32 accumulator in TMEM over all its tiles.
+#pragma once
+#include "svs_common.cuh"
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+
+namespace svs {
+namespace tc {
+
+constexpr int kTile = 128;            // points per tile = MMA M
+constexpr int kBlk = 16384;           // one 64-column block of a 128-row tile image
+constexpr int kMaxKB = 5;             // widest A operand: 320 columns
+constexpr int kWSlots = 2, kWSlot = 32768;
+constexpr int kXSlots = 3, kXSlot = 16384;
+constexpr int kThreads = 640;         // 4 control warps + 16 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kStashLd = 40;          // fp32 per row: skip-branch / PE-gradient stash (<= 39 + pad)
+constexpr int kMaxSteps = 11;
+constexpr int kMaxImgs = 36;
+constexpr int kMaxColsum = 9;
+constexpr int kColsumW = 320;
+
+// shared memory map (bytes)
+constexpr int kOffA = 0;
+constexpr int kOffW = kOffA + kMaxKB * kBlk;                // 81920
+constexpr int kOffX = kOffW + kWSlots * kWSlot;             // 147456
+constexpr int kOffStash = kOffX + kXSlots * kXSlot;         // 196608
+constexpr int kOffVec = kOffStash + kTile * kStashLd * 4;   // 217088 : bias / row-vector of the step (256 fp32)
+constexpr int kOffVec2 = kOffVec + 1024;                    // second row vector (256 fp32)
+constexpr int kOffColsum = kOffVec2 + 1024;                 // kMaxColsum x 256 fp32 per-CTA column sums
+constexpr int kOffBar = kOffColsum + kMaxColsum * kColsumW * 4;  // 230656
+constexpr int kSmemBytes = kOffBar + 256;                        // 230912 <= 232448
+
+enum TcEpi : int32_t {
+  EP_SOFTPLUS = 0,  // A' = softplus(acc + b) * scale ; columns >= n_valid: PE(x) * scale (TC_PEFILL) or 0
+  EP_SDF = 1,       // sdf[p] = min(acc_0 + b_0, sphere)                    (get_sdf_vals)
+  EP_Y = 2,         // y[p, y_col + n] = acc + b
+  EP_REVERSE = 3,   // p = acc*scale ; n < n_split: A' = s(h*hscale) p ; else stash[n - n_split] = p
+  EP_PEGRAD = 4,    // stash += acc ; g = J_PE^T stash ; sphere clamp ; writes sdf, grad
+  EP_RELU = 5,      // A' = relu(acc + b)
+  EP_RGB = 6,       // rgb[p, n] = sigmoid(acc + b), n < n_valid
+  EP_RELU_BWD = 7,  // A' = h > 0 ? acc : 0
+  EP_DFEAT = 8,     // d_feat[p, n] = acc
+  EP_DSMALL = 9,    // d_normals[p, j] = acc[small_off + j]
+  EP_TANGENT = 10,  // s = s(h*hscale) ; zeta = beta (1-s) U acc -> image out2 ; A' = s acc scale
+  EP_BACKWARD = 11  // A' = s(h*hscale) acc scale + zeta
+};
+
+enum TcPrologue : int32_t {
+  PRO_PE = 0,          // A = PE(x)
+  PRO_LOAD_ULAST = 1,  // A = h_8 image ; A' = s(h_8) * w_row
+  PRO_RENDER_IN = 2,   // A = [feat(F) | points, PE(view), normals]
+  PRO_SIGMOID_BWD = 3, // A = d_rgb rgb (1 - rgb)
+  PRO_PE_JVP = 4,      // A = J_PE(x) (w d_grad)
+  PRO_DY = 5           // A = dy (+ w d_sdf in column 0)
+};
+
+constexpr int32_t TC_PEFILL = 1;   // step flag: fill pad columns of A' with PE(x)*scale (skip connection)
+constexpr int32_t TC_QFILL = 2;    // step flag: fill pad columns of A' with (J_PE(x) w d_grad)*scale (tangent of the skip)
+
+struct TcStep {
+  const uint8_t* w;    // KB blocks of n_pad x 128 bytes
+  const float* bias;   // fp32[n_valid] or nullptr
+  int32_t KB, n_pad, n_valid, epi;
+  float scale, hscale;
+  int32_t n_split;
+  int32_t aux1, aux2;  // image ids or -1
+  int32_t save;        // image id A' is saved to, or -1
+  int32_t out2;        // EP_TANGENT: image id of zeta
+  int32_t next_kb;     // 64-column blocks of A' to produce (0: the step has no A')
+  int32_t flags;
+  int32_t colsum;      // >= 0: add the column sums of A' into colsum slot
+  int32_t y_col;       // EP_Y: first output column ; EP_DSMALL: first accumulator column
+};
+
+struct TcImg {
+  uint8_t* base;
+  int64_t tile_bytes;
+};
+
+struct TcChain {
+  TcStep st[kMaxSteps];
+  TcImg img[kMaxImgs];
+  int32_t n_steps, prologue, pro_kb, pro_save;  // pro_save: image id the prologue's A is saved to, or -1
+  int32_t pro_img;                              // PRO_LOAD_ULAST: image id loaded into A
+  int32_t pro_colsum;                           // >= 0: column sums of the prologue's A
+  const float* pro_vec;                         // PRO_LOAD_ULAST: fp32 row vector (W_last[0,:])
+  int64_t P;
+  int32_t n_tiles;
+  // geometry of the SDF net input
+  const float* x;
+  int32_t d_in, n_freqs;
+  float radius, sph_scale;
+  int32_t clamp;
+  // fp32 inputs / outputs (row-major)
+  float* y; int32_t ldy;
+  const float* yin;            // raw sdf column source for the clamp (reverse / tangent / backward chains)
+  float* sdf; float* grad;
+  const float* dy; const float* d_sdf; const float* d_grad; int32_t dy_cols;
+  // rendering net
+  const float* points; const float* view; const float* normals; const float* feat; int32_t ld_feat;
+  int32_t view_freqs, idr, F;
+  float* rgb; const float* rgb_in; const float* d_rgb; int32_t n_rgb;
+  float* d_normals; float* d_feat; int32_t ld_dfeat;
+  float* colsum_out[kMaxColsum]; int32_t colsum_n[kMaxColsum];
+  // backward chains: gradients are carried multiplied by grad_scale(amax, amax_target) (fp16 range)
+  const uint32_t* amax; float amax_target;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Operand storage format: IEEE fp16 (10-bit mantissa: the precision class of the TF32 GEMMs the reference ran with
+// on Ampere; bf16's 7 bits are not enough behind Softplus(beta=100)).  Conversions saturate instead of producing inf.
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// power-of-two scale that brings the largest upstream gradient (|.| max as float bits in *amax) to ~target
+__device__ __forceinline__ float grad_scale(const uint32_t* amax, float target) {
+  if (!amax) return 1.f;
+  float a = __uint_as_float(*amax);
+  if (!(a > 0.f) || !isfinite(a)) return 1.f;
+  float e = floorf(log2f(target / a));
+  e = fminf(fmaxf(e, -40.f), 40.f);
+  return exp2f(e);
+}
+
+// byte offset of the 16-byte chunk `chunk` (0..7) of row m inside a 64-column block
+__device__ __forceinline__ uint32_t chunk_off(int m, int chunk) {
+  return (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u + (uint32_t)((chunk ^ (m & 7)) << 4);
+}
+// 16 consecutive columns (quarter `cq` of a block) of row m: write / read
+__device__ __forceinline__ void st_row16(uint8_t* blk, int m, int cq, const float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u;
+    u.x = pack_h2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_h2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_h2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_h2(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(blk + chunk_off(m, cq * 2 + i)) = u;
+  }
+}
+__device__ __forceinline__ void ld_row16(const uint8_t* blk, int m, int cq, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u = *reinterpret_cast<const uint4*>(blk + chunk_off(m, cq * 2 + i));
+    float2 f;
+    f = unpack_h2(u.x); v[8 * i + 0] = f.x; v[8 * i + 1] = f.y;
+    f = unpack_h2(u.y); v[8 * i + 2] = f.x; v[8 * i + 3] = f.y;
+    f = unpack_h2(u.z); v[8 * i + 4] = f.x; v[8 * i + 5] = f.y;
+    f = unpack_h2(u.w); v[8 * i + 6] = f.x; v[8 * i + 7] = f.y;
+  }
+}
+
+constexpr float kSpK1 = 144.26950408889634f;     // 100 * log2(e)
+constexpr float kSpK2 = 0.006931471805599453f;   // ln(2) / 100
+constexpr float kSpThr = 28.853900817779268f;    // 20 * log2(e): Softplus threshold (network.py:69, torch default 20)
+// Softplus(beta=100, threshold 20) * scale with one ex2 + one lg2 (abs. error of the lg2(1+e) form <= 1e-9)
+__device__ __forceinline__ float softplus100_fast(float z, float scale) {
+  float t = z * kSpK1;
+  float l = lg2_approx(1.0f + ex2_approx(fminf(t, kSpThr)));
+  return (t > kSpThr) ? z * scale : l * (kSpK2 * scale);
+}
+// sigma'(z) recovered from h = softplus(z): 1 - exp(-100 h)
+__device__ __forceinline__ float dsoftplus_h(float h) { return 1.0f - ex2_approx(-kSpK1 * h); }
+
+__device__ __forceinline__ float pe_col(const float (&xv)[4], int d_in, int n_freqs, int c) {
+  if (c < d_in) return xv[c];
+  int t = c - d_in;
+  int k = t / (2 * d_in);
+  if (k >= n_freqs) return 0.f;
+  int rem = t - k * 2 * d_in;
+  int fn = rem / d_in, dim = rem - fn * d_in;
+  float arg = xv[dim] * (float)(1 << k);
+  return fn ? cosf(arg) : sinf(arg);
+}
+// d PE_c / d x_dim(c)
+__device__ __forceinline__ float pe_dcol(const float (&xv)[4], int d_in, int n_freqs, int c, int* dim_out) {
+  if (c < d_in) { *dim_out = c; return 1.f; }
+  int t = c - d_in;
+  int k = t / (2 * d_in);
+  if (k >= n_freqs) { *dim_out = 0; return 0.f; }
+  int rem = t - k * 2 * d_in;
+  int fn = rem / d_in, dim = rem - fn * d_in;
+  float f = (float)(1 << k);
+  float arg = xv[dim] * f;
+  *dim_out = dim;
+  return fn ? (-f * sinf(arg)) : (f * cosf(arg));
+}
+
+__device__ __forceinline__ float clamp_w(float y0, float sphere) { return (y0 < sphere) ? 1.f : ((y0 == sphere) ? 0.5f : 0.f); }
+
+// per-column sums over the 32 lanes of v[0..15]; lanes i and i+16 both return column i's sum
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      float send = upper ? v[i] : v[i + w];
+      float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+struct Bars {
+  uint64_t w_full[kWSlots], w_empty[kWSlots], x_full[kXSlots], x_empty[kXSlots], a_ready[kMaxKB], acc_full, a_load;
+  uint32_t tmem;
+};
+
+__host__ __device__ constexpr uint32_t epi_bit(int e) { return 1u << e; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// the chain kernel; EPI / PRO select which epilogues / prologue are compiled into an instantiation
+// ---------------------------------------------------------------------------------------------------------------
+template <uint32_t EPI, int PRO>
+__global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChain ch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + kOffA;
+  uint8_t* sW = smem + kOffW;
+  uint8_t* sX = smem + kOffX;
+  float* stash = reinterpret_cast<float*>(smem + kOffStash);
+  float* vec = reinterpret_cast<float*>(smem + kOffVec);
+  float* colsum = reinterpret_cast<float*>(smem + kOffColsum);
+  Bars* bars = reinterpret_cast<Bars*>(smem + kOffBar);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < kXSlots; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kEpiWarps); }
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->a_ready[i], kEpiWarps);
+    mbar_init(&bars->acc_full, 1);
+    mbar_init(&bars->a_load, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < kMaxColsum * kColsumW; i += kThreads) colsum[i] = 0.f;
+  if (warp == 2) tmem_alloc(&bars->tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem;
+
+  if (warp == 0) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          const uint32_t bytes = (uint32_t)st.n_pad * 128u;
+          for (int kb = 0; kb < st.KB; ++kb, ++seq) {
+            const int slot = seq % kWSlots;
+            const uint32_t use = seq / kWSlots;
+            mbar_wait(&bars->w_empty[slot], (use & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
+            bulk_g2s(sW + slot * kWSlot, st.w + (size_t)kb * bytes, bytes, &bars->w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: block kb of step s is issued as soon as the epilogue of step s-1 has rewritten it =====
+    if (lane == 0) {
+      uint32_t seq = 0, n_step = 0, a_par = 0;
+      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        for (int s = 0; s < ch.n_steps; ++s, ++n_step) {
+          const TcStep& st = ch.st[s];
+          const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
+          const uint32_t acc = tmem + (n_step & 1) * 256;
+          for (int kb = 0; kb < st.KB; ++kb, ++seq) {
+            mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+            a_par ^= 1u << kb;
+            const int slot = seq % kWSlots;
+            const uint32_t use = seq / kWSlots;
+            mbar_wait(&bars->w_full[slot], use & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(sA + kb * kBlk), b0 = smem_u32(sW + slot * kWSlot);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              umma_f16(acc, make_smem_desc(a0 + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc,
+                       (kb | j) != 0);
+            umma_commit(&bars->w_empty[slot]);
+          }
+          umma_commit(&bars->acc_full);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== aux producer =====
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          if (st.aux1 < 0) continue;
+          const int nchunk = (st.n_pad + 63) >> 6;
+          for (int c = 0; c < nchunk; ++c) {
+            for (int a = 0; a < 2; ++a) {
+              const int id = a ? st.aux2 : st.aux1;
+              if (id < 0) continue;
+              const int slot = seq % kXSlots;
+              const uint32_t use = seq / kXSlots;
+              ++seq;
+              mbar_wait(&bars->x_empty[slot], (use & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars->x_full[slot], kBlk);
+              bulk_g2s(sX + slot * kXSlot, ch.img[id].base + (size_t)t * ch.img[id].tile_bytes + (size_t)c * kBlk, kBlk,
+                       &bars->x_full[slot]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps =====
+    const int ew = warp - 4, q = ew & 3, cq = ew >> 2;
+    const int m = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const bool leader = (et == 0);
+    const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t n_acc = 0, xseq = 0, n_load = 0;
+    const float gs = grad_scale(ch.amax, ch.amax_target);
+    const float inv_gs = 1.0f / gs;
+    const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
+    const bool clamp_on = ch.clamp && ch.radius > 0.f;
+
+    for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+      const int64_t p = (int64_t)t * kTile + m;
+      const bool live = p < ch.P;
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ch.x && live)
+        for (int d = 0; d < ch.d_in; ++d) xv[d] = ch.x[p * ch.d_in + d];
+      // sphere clamp of the point (get_outputs / get_sdf_vals, network.py:108-112,128-130)
+      float sphere = 0.f, cw = 1.f, nrm = 1.f;
+      if (clamp_on) {
+        float n2 = 0.f;
+        for (int d = 0; d < ch.d_in; ++d) n2 += xv[d] * xv[d];
+        nrm = sqrtf(n2);
+        sphere = ch.sph_scale * (ch.radius - nrm);
+        if (ch.yin && live) cw = clamp_w(ch.yin[p * ch.ldy], sphere);
+      }
+      float dg[4] = {0.f, 0.f, 0.f, 0.f};  // grad_scale * w * dL/dgrad of the point (tangent sweep)
+      if (PRO == PRO_PE_JVP && ch.d_grad && live)
+        for (int d = 0; d < ch.d_in; ++d) dg[d] = gs * cw * ch.d_grad[p * ch.d_in + d];
+      // the previous tile's last save must have left the A tile before the prologue overwrites it
+      if (leader) bulk_wait_read<0>();
+      if (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD)))
+        for (int i = cq; i < kStashLd; i += 4) stash[m * kStashLd + i] = 0.f;
+      if (PRO == PRO_LOAD_ULAST) {
+        if (et < 256) vec[et] = ch.pro_vec[et];
+        if (leader) {
+          const uint32_t bytes = (uint32_t)ch.pro_kb * kBlk;
+          mbar_arrive_expect_tx(&bars->a_load, bytes);
+          bulk_g2s(sA, ch.img[ch.pro_img].base + (size_t)t * ch.img[ch.pro_img].tile_bytes, bytes, &bars->a_load);
+        }
+      }
+      named_bar_sync(1, kEpiThreads);
+
+      // ---------------- prologue: build the first A operand, one 64-column block at a time ----------------
+      if (PRO == PRO_LOAD_ULAST) {
+        mbar_wait(&bars->a_load, n_load & 1);
+        ++n_load;
+      }
+      for (int b = 0; b < ch.pro_kb; ++b) {
+        float v[16];
+        const int c0 = b * 64 + cq * 16;
+        if (PRO == PRO_PE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_col(xv, ch.d_in, ch.n_freqs, c0 + i) : 0.f;
+        } else if (PRO == PRO_LOAD_ULAST) {
+          ld_row16(sA + b * kBlk, m, cq, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = dsoftplus_h(v[i]) * vec[c0 + i];
+        } else if (PRO == PRO_RENDER_IN) {
+          const int nfb = ch.F >> 6;  // feature blocks, then one block [points(3) if idr, PE(view), normals(3) if idr]
+          if (b < nfb) {
+            const float4* src = reinterpret_cast<const float4*>(ch.feat + p * ch.ld_feat + c0);
+            const bool al = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) {
+                if (al) f = src[i];
+                else { const float* sp = ch.feat + p * ch.ld_feat + c0 + 4 * i; f = make_float4(sp[0], sp[1], sp[2], sp[3]); }
+              }
+              v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+            }
+          } else {
+            const int pe_v = 3 * (1 + 2 * ch.view_freqs);
+            const int o_view = ch.idr ? 3 : 0, o_n = o_view + pe_v, n_small = o_n + (ch.idr ? 3 : 0);
+            float vv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live) { vv[0] = ch.view[p * 3]; vv[1] = ch.view[p * 3 + 1]; vv[2] = ch.view[p * 3 + 2]; }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = cq * 16 + i;
+              float r = 0.f;
+              if (live && c < n_small) {
+                if (c < o_view) r = ch.points[p * 3 + c];
+                else if (c < o_n) r = pe_col(vv, 3, ch.view_freqs, c - o_view);
+                else r = ch.normals[p * 3 + (c - o_n)];
+              }
+              v[i] = r;
+            }
+          }
+        } else if (PRO == PRO_SIGMOID_BWD) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            float r = 0.f;
+            if (live && c < ch.n_rgb) {
+              float sg = ch.rgb_in[p * ch.n_rgb + c];
+              r = gs * ch.d_rgb[p * ch.n_rgb + c] * sg * (1.f - sg);
+            }
+            v[i] = r;
+          }
+        } else if (PRO == PRO_PE_JVP) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            float r = 0.f;
+            if (live && c < pe_w) {
+              int dim;
+              float j = pe_dcol(xv, ch.d_in, ch.n_freqs, c, &dim);
+              r = j * dg[dim];
+            }
+            v[i] = r;
+          }
+        } else if (PRO == PRO_DY) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + i;
+            float r = 0.f;
+            if (live && c < ch.dy_cols) {
+              if (ch.dy) r = ch.dy[p * ch.ldy + c];
+              if (c == 0 && ch.d_sdf) r += cw * ch.d_sdf[p];
+              r *= gs;
+            }
+            v[i] = r;
+          }
+        }
+        st_row16(sA + b * kBlk, m, cq, v);
+        if (ch.pro_colsum >= 0) {
+          float cs = warp_colsum16(v, lane);
+          if (lane < 16) atomicAdd(&colsum[ch.pro_colsum * kColsumW + c0 + lane], cs);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->a_ready[b]);
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (leader && ch.pro_save >= 0) {
+        bulk_s2g(ch.img[ch.pro_save].base + (size_t)t * ch.img[ch.pro_save].tile_bytes, sA, (uint32_t)ch.pro_kb * kBlk);
+        bulk_commit();
+      }
+
+      // ---------------- steps ----------------
+      for (int s = 0; s < ch.n_steps; ++s) {
+        const TcStep& st = ch.st[s];
+        const bool has_next = s + 1 < ch.n_steps;
+        const bool writes_a = st.next_kb > 0;
+        // stage the step's bias, wait for the accumulator, make sure the last save has left the A tile
+        if (st.bias && et < 256) vec[et] = (et < st.n_valid) ? st.bias[et] : 0.f;
+        const uint32_t tm_acc = tm_row + (n_acc & 1) * 256;
+        mbar_wait(&bars->acc_full, n_acc & 1);
+        ++n_acc;
+        tc_fence_after();
+        if (leader) bulk_wait_read<0>();
+        named_bar_sync(1, kEpiThreads);
+        if (!writes_a && has_next) {
+          // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
+          if (lane == 0)
+            for (int c = 0; c < ch.st[s + 1].KB; ++c) mbar_arrive(&bars->a_ready[c]);
+        }
+
+        const int nchunk_acc = (st.n_pad + 63) >> 6;
+        const int nchunk = max(nchunk_acc, st.next_kb);
+        for (int c = 0; c < nchunk; ++c) {
+          const int col0 = c * 64 + cq * 16;
+          float acc[16];
+          if (col0 < st.n_pad) {
+            uint32_t r[16];
+            tmem_ld_32x16(tm_acc + (uint32_t)col0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+          }
+          // aux tiles of this chunk
+          float a1[16], a2[16];
+          int slot1 = -1, slot2 = -1;
+          if (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_RELU_BWD) | epi_bit(EP_TANGENT) | epi_bit(EP_BACKWARD))) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a2[i] = 0.f;
+            if (c < nchunk_acc && st.aux1 >= 0) {
+              slot1 = xseq % kXSlots;
+              mbar_wait(&bars->x_full[slot1], (xseq / kXSlots) & 1);
+              ++xseq;
+              ld_row16(sX + slot1 * kXSlot, m, cq, a1);
+              if (st.aux2 >= 0) {
+                slot2 = xseq % kXSlots;
+                mbar_wait(&bars->x_full[slot2], (xseq / kXSlots) & 1);
+                ++xseq;
+                ld_row16(sX + slot2 * kXSlot, m, cq, a2);
+              }
+            }
+          }
+          float o[16];
+          const bool full = col0 + 16 <= st.n_valid;   // no pad columns in this thread's 16
+          if ((EPI & epi_bit(EP_SOFTPLUS)) && st.epi == EP_SOFTPLUS) {
+            if (full) {
+              const float4* b4 = reinterpret_cast<const float4*>(vec + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 b = b4[i];
+                o[4 * i + 0] = softplus100_fast(acc[4 * i + 0] + b.x, st.scale);
+                o[4 * i + 1] = softplus100_fast(acc[4 * i + 1] + b.y, st.scale);
+                o[4 * i + 2] = softplus100_fast(acc[4 * i + 2] + b.z, st.scale);
+                o[4 * i + 3] = softplus100_fast(acc[4 * i + 3] + b.w, st.scale);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                float r = 0.f;
+                if (n < st.n_valid) r = softplus100_fast(acc[i] + vec[n & 255], st.scale);
+                else if (st.flags & TC_PEFILL) r = pe_col(xv, ch.d_in, ch.n_freqs, n - st.n_valid) * st.scale;
+                o[i] = r;
+              }
+            }
+          } else if ((EPI & epi_bit(EP_SDF)) && st.epi == EP_SDF) {
+            if (col0 == 0 && live) {
+              float y0 = acc[0] + vec[0];
+              if (clamp_on) y0 = fminf(y0, sphere);
+              ch.sdf[p] = y0;
+            }
+          } else if ((EPI & epi_bit(EP_Y)) && st.epi == EP_Y) {
+            if (live) {
+              float* dst = ch.y + p * ch.ldy + st.y_col + col0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < st.n_valid) dst[i] = acc[i] + vec[(col0 + i) & 255];
+            }
+          } else if ((EPI & epi_bit(EP_REVERSE)) && st.epi == EP_REVERSE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = col0 + i;
+              const float pv = acc[i] * st.scale;
+              float r = 0.f;
+              if (n < st.n_split) r = dsoftplus_h(a1[i] * st.hscale) * pv;
+              else if (n < st.n_valid) stash[m * kStashLd + (n - st.n_split)] = pv;
+              o[i] = r;
+            }
+          } else if ((EPI & epi_bit(EP_PEGRAD)) && st.epi == EP_PEGRAD) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < st.n_valid) stash[m * kStashLd + col0 + i] += acc[i];
+          } else if ((EPI & epi_bit(EP_RELU)) && st.epi == EP_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = col0 + i;
+              o[i] = (n < st.n_valid) ? fmaxf(acc[i] + vec[n & 255], 0.f) : 0.f;
+            }
+          } else if ((EPI & epi_bit(EP_RGB)) && st.epi == EP_RGB) {
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + __expf(-(acc[i] + vec[n & 255])));
+              }
+            }
+          } else if ((EPI & epi_bit(EP_RELU_BWD)) && st.epi == EP_RELU_BWD) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = (a1[i] > 0.f && col0 + i < st.n_valid) ? acc[i] : 0.f;
+          } else if ((EPI & epi_bit(EP_DFEAT)) && st.epi == EP_DFEAT) {
+            if (live && ch.d_feat) {
+              float* dst = ch.d_feat + p * ch.ld_dfeat + col0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < st.n_valid) dst[i] = acc[i] * inv_gs;
+            }
+          } else if ((EPI & epi_bit(EP_DSMALL)) && st.epi == EP_DSMALL) {
+            if (live && ch.d_normals) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int j = col0 + i - st.y_col;
+                if (j >= 0 && j < 3) ch.d_normals[p * 3 + j] = acc[i] * inv_gs;
+              }
+            }
+          } else if ((EPI & epi_bit(EP_TANGENT)) && st.epi == EP_TANGENT) {
+            float z[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = col0 + i;
+              const float sg = dsoftplus_h(a1[i] * st.hscale);
+              const bool ok = n < st.n_valid;
+              z[i] = ok ? 100.0f * (1.0f - sg) * a2[i] * acc[i] : 0.f;
+              o[i] = ok ? sg * acc[i] * st.scale : 0.f;
+            }
+            if (!full && (st.flags & TC_QFILL)) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                if (n >= st.n_valid && n - st.n_valid < pe_w) {
+                  int dim;
+                  float j = pe_dcol(xv, ch.d_in, ch.n_freqs, n - st.n_valid, &dim);
+                  o[i] = live ? j * dg[dim] * st.scale : 0.f;
+                }
+              }
+            }
+            // zeta overwrites the U block in its aux slot and leaves through a bulk store
+            if (slot2 >= 0) st_row16(sX + slot2 * kXSlot, m, cq, z);
+          } else if ((EPI & epi_bit(EP_BACKWARD)) && st.epi == EP_BACKWARD) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float sg = dsoftplus_h(a1[i] * st.hscale);
+              o[i] = (col0 + i < st.n_valid) ? sg * acc[i] * st.scale + a2[i] : 0.f;
+            }
+          }
+          if (writes_a && c < st.next_kb) {
+            st_row16(sA + c * kBlk, m, cq, o);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0 && has_next) mbar_arrive(&bars->a_ready[c]);
+            if (st.colsum >= 0) {
+              float cs = warp_colsum16(o, lane);
+              if (lane < 16) atomicAdd(&colsum[st.colsum * kColsumW + col0 + lane], cs);
+            }
+          }
+          // release the aux slots
+          if (slot1 >= 0) {
+            if ((EPI & epi_bit(EP_TANGENT)) && st.epi == EP_TANGENT) {
+              // all warps have rewritten slot2 -> one bulk store, then both slots go back to the producer
+              fence_proxy_async();
+              named_bar_sync(2, kEpiThreads);
+              if (leader) {
+                bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk,
+                         sX + slot2 * kXSlot, kBlk);
+                bulk_commit();
+                bulk_wait_read<0>();
+              }
+              named_bar_sync(2, kEpiThreads);
+            } else {
+              __syncwarp();
+            }
+            if (lane == 0) {
+              mbar_arrive(&bars->x_empty[slot1]);
+              if (slot2 >= 0) mbar_arrive(&bars->x_empty[slot2]);
+            }
+          }
+        }
+        if ((EPI & epi_bit(EP_PEGRAD)) && st.epi == EP_PEGRAD) {
+          // stash now holds p_0 + e for all PE columns of the row: g = J_PE^T (p_0 + e), sphere clamp of sdf and g
+          named_bar_sync(2, kEpiThreads);
+          if (cq == 0 && live) {
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < pe_w; ++c) {
+              int dim;
+              float j = pe_dcol(xv, ch.d_in, ch.n_freqs, c, &dim);
+              g[dim] += j * stash[m * kStashLd + c];
+            }
+            float y0 = ch.yin[p * ch.ldy];
+            float out_sdf = y0;
+            if (clamp_on) {
+              out_sdf = fminf(y0, sphere);
+              for (int d = 0; d < ch.d_in; ++d) g[d] = cw * g[d] + (1.f - cw) * (-ch.sph_scale * xv[d] / nrm);
+            }
+            if (ch.sdf) ch.sdf[p] = out_sdf;
+            if (ch.grad)
+              for (int d = 0; d < ch.d_in; ++d) ch.grad[p * ch.d_in + d] = g[d];
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(1, kEpiThreads);
+        if (leader && st.save >= 0) {
+          bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes, sA, (uint32_t)st.next_kb * kBlk);
+          bulk_commit();
+        }
+      }
+    }
+    if (leader) bulk_wait_all<0>();
+    // flush the per-CTA column sums (bias gradients, dW_last[0,:])
+    named_bar_sync(1, kEpiThreads);
+    for (int k = 0; k < kMaxColsum; ++k) {
+      if (!ch.colsum_out[k]) continue;
+      for (int i = et; i < ch.colsum_n[k]; i += kEpiThreads) atomicAdd(&ch.colsum_out[k][i], colsum[k * kColsumW + i] * inv_gs);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+constexpr uint32_t kEpiFwd = epi_bit(EP_SOFTPLUS) | epi_bit(EP_SDF) | epi_bit(EP_Y);
+constexpr uint32_t kEpiRev = epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD);
+constexpr uint32_t kEpiRenderFwd = epi_bit(EP_RELU) | epi_bit(EP_RGB);
+constexpr uint32_t kEpiRenderBwd = epi_bit(EP_RELU_BWD) | epi_bit(EP_DFEAT) | epi_bit(EP_DSMALL);
+constexpr uint32_t kEpiTan = epi_bit(EP_TANGENT);
+constexpr uint32_t kEpiBwd = epi_bit(EP_BACKWARD);
+
+}  // namespace tc
+}  // namespace svs

@@ -26,7 +26,7 @@ class NetHandle(object):
         self.desc = desc
         self.layers = layers            # list of (g or None, v, b) nn.Parameters, layer order
         self.engine = engine
-        self.wbuf_floats = int(L.load().svs_mlp_wbuf_floats(desc))
+        self.wbuf_floats = int(L.load().svs_mlp_wbuf_floats(desc, engine))
         if self.wbuf_floats < 0:
             raise L.SvsError('bad MLP descriptor: %s' % L.load().svs_last_error().decode())
         self.ldy = int(L.load().svs_sdf_ldy(desc))
@@ -80,7 +80,7 @@ def sdf_forward_nograd(net, x, want_y, want_sdf):
     P = x.shape[0]
     dev = x.device
     wbuf = net.prepare(dev)
-    ws = _f32(max(1, int(L.load().svs_sdf_ws_floats(net.desc, P, 0))), device=dev)
+    ws = _f32(max(1, int(L.load().svs_sdf_ws_floats(net.desc, P, 0, net.engine))), device=dev)
     y = _f32(P, net.ldy, device=dev) if want_y else None
     sdf = _f32(P, 1, device=dev) if want_sdf else None
     if P == 0:
@@ -105,8 +105,8 @@ class SdfOutputsFn(torch.autograd.Function):
         y = _f32(P, net.ldy, device=dev)
         sdf = _f32(P, 1, device=dev)
         grad = _f32(P, net.desc.d_in, device=dev) if (want_grad or train) else None
-        saved = _f32(max(1, int(lib.svs_sdf_saved_floats(net.desc, P))), device=dev) if train else None
-        ws = _f32(max(1, int(lib.svs_sdf_ws_floats(net.desc, P, 0 if train else 1))), device=dev)
+        saved = _f32(max(1, int(lib.svs_sdf_saved_floats(net.desc, P, net.engine))), device=dev) if train else None
+        ws = _f32(max(1, int(lib.svs_sdf_ws_floats(net.desc, P, 0 if train else 1, net.engine))), device=dev)
         L.call('svs_sdf_outputs_forward', net.desc, ptr(wbuf), ptr(x), P, 1 if clamp else 0, ptr(y), ptr(sdf),
                ptr(grad), ptr(saved), ptr(ws), net.engine, L.stream())
         ctx.net, ctx.clamp, ctx.P = net, clamp, P
@@ -124,7 +124,7 @@ class SdfOutputsFn(torch.autograd.Function):
         dev = x.device
         lib = L.load()
         dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
-        ws = _f32(max(1, int(lib.svs_sdf_bwd_ws_floats(net.desc, P))), device=dev)
+        ws = _f32(max(1, int(lib.svs_sdf_bwd_ws_floats(net.desc, P, net.engine))), device=dev)
         dy, d_sdf, d_grad = _contig(dy), _contig(d_sdf), _contig(d_grad)
         L.call('svs_sdf_outputs_backward', net.desc, ptr(wbuf), ptr(x), P, 1 if ctx.clamp else 0, ptr(saved), ptr(y),
                ptr(dy), ptr(d_sdf), ptr(d_grad), ptr(dwbuf), ptr(ws), net.engine, L.stream())
@@ -155,7 +155,7 @@ class RenderFn(torch.autograd.Function):
         fptr = f.data_ptr() + 4 * feat_col
         lib = L.load()
         wbuf = net.prepare(dev)
-        saved = _f32(max(1, int(lib.svs_render_saved_floats(net.desc, P))), device=dev)
+        saved = _f32(max(1, int(lib.svs_render_saved_floats(net.desc, P, net.engine))), device=dev)
         rgb = _f32(P, net.desc.out_dim[net.desc.n_layers - 1], device=dev)
         L.call('svs_render_forward', net.desc, ptr(wbuf), ptr(pts), ptr(view_dirs), ptr(nrm), fptr, ld_feat, P,
                ptr(rgb), ptr(saved), net.engine, L.stream())
@@ -171,7 +171,7 @@ class RenderFn(torch.autograd.Function):
         dev = rgb.device
         lib = L.load()
         dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
-        ws = _f32(max(1, int(lib.svs_render_ws_floats(net.desc, P))), device=dev)
+        ws = _f32(max(1, int(lib.svs_render_ws_floats(net.desc, P, net.engine))), device=dev)
         d_normals = _f32(P, 3, device=dev) if ctx.idr else None
         d_feat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
         L.call('svs_render_backward', net.desc, ptr(wbuf), P, ptr(saved), ptr(rgb), ptr(d_rgb.contiguous()),

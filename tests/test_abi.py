@@ -31,7 +31,7 @@ def test_ctypes_table_matches_header():
 
 def test_abi_version_and_engine_query():
     lib = L.load()
-    assert lib.svs_abi_version() == 1
+    assert lib.svs_abi_version() == 2
     assert lib.svs_has_engine(L.ENGINE_FP32) == 1
 
 
@@ -39,12 +39,16 @@ def test_descriptor_validation_needs_no_gpu():
     lib = L.load()
     d = L.make_desc(L.NET_SDF, [39, 256, 256, 256, 256, 256, 256, 256, 256],
                     [256, 256, 256, 217, 256, 256, 256, 256, 257], d_in=3, n_freqs=6, skip_layer=4)
-    n = lib.svs_mlp_wbuf_floats(d)
+    n = lib.svs_mlp_wbuf_floats(d, L.ENGINE_FP32)
     assert n == sum(o * ((i + 3) // 4 * 4) + (o + 3) // 4 * 4 for i, o in
                     zip([39, 256, 256, 256, 256, 256, 256, 256, 256], [256, 256, 256, 217, 256, 256, 256, 256, 257]))
     assert lib.svs_sdf_ldy(d) == 260
+    # the tcgen05 engine appends the bf16 weight images (forward + transposed) to the fp32 block
+    nb = lib.svs_mlp_wbuf_floats(d, L.ENGINE_TC)
+    assert nb > n and lib.svs_has_engine(L.ENGINE_TC) == 1
+    assert lib.svs_sdf_saved_floats(d, 1000, L.ENGINE_TC) == 8 * (1 + 8 * 4 + 8 * 4) * 16384 // 4
     bad = L.make_desc(L.NET_SDF, [39, 256], [256, 257], d_in=3, n_freqs=5)
-    assert lib.svs_mlp_wbuf_floats(bad) == -1
+    assert lib.svs_mlp_wbuf_floats(bad, L.ENGINE_FP32) == -1
     assert b'PE width' in lib.svs_last_error()
 
 

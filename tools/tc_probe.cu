@@ -10,6 +10,7 @@
 
 #include <vector>
 
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 using namespace svs::tc;
@@ -26,7 +27,7 @@ using namespace svs::tc;
 // mode 0: K-major.  A image: 128 rows x K cols; B image: N rows x K cols.  C = A * B^T  (128 x N)
 // mode 1: MN-major. A image: P rows x 128 cols (uses cols [0,128)); B image: P rows x N cols. D = A^T * B (128 x N)
 __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes,
-                                                   const uint8_t* __restrict__ b_img, int b_bytes, int mode, int N,
+                                                   const uint8_t* __restrict__ b_img, int b_bytes, int mode, int afmt, int bfmt, int N,
                                                    int K, int a_rows, int b_rows, float* __restrict__ C) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_load, bar_mma;
@@ -51,14 +52,14 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
     mbar_wait(&bar_load, 0);
     tc_fence_after();
     if (mode == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      const uint32_t idesc = (make_idesc_bf16(128, N, 0, 0) & ~((7u << 7) | (7u << 10))) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10);
       for (int j = 0; j < K / 16; ++j) {
         uint64_t da = make_smem_desc(smem_u32(sa) + (j >> 2) * (a_rows * 128) + (j & 3) * 32, 0, 1024);
         uint64_t db = make_smem_desc(smem_u32(sb) + (j >> 2) * (b_rows * 128) + (j & 3) * 32, 0, 1024);
         umma_f16(tmem, da, db, idesc, j > 0);
       }
     } else {
-      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      const uint32_t idesc = (make_idesc_bf16(128, N, 1, 1) & ~((7u << 7) | (7u << 10))) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10);
       for (int j = 0; j < K / 16; ++j) {  // K = number of points (rows of the images)
         uint64_t da = make_smem_desc(smem_u32(sa) + j * 2048, a_rows * 128, 1024);
         uint64_t db = make_smem_desc(smem_u32(sb) + j * 2048, b_rows * 128, 1024);
@@ -84,16 +85,21 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* __restrict__ 
 
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-static void build_image(const std::vector<float>& m, int rows, int cols, std::vector<uint8_t>& img) {
+static void build_image(const std::vector<float>& m, int rows, int cols, std::vector<uint8_t>& img, int fmt) {
   img.assign((size_t)rows * cols * 2, 0);
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
-      __nv_bfloat16 v = __float2bfloat16(m[(size_t)r * cols + c]);
-      memcpy(&img[img_off(r, c, rows)], &v, 2);
+      if (fmt == 1) {
+        __nv_bfloat16 v = __float2bfloat16(m[(size_t)r * cols + c]);
+        memcpy(&img[img_off(r, c, rows)], &v, 2);
+      } else {
+        __half v = __float2half(m[(size_t)r * cols + c]);
+        memcpy(&img[img_off(r, c, rows)], &v, 2);
+      }
     }
 }
 
-static int run(int mode, int N, int K) {
+static int run(int mode, int N, int K, int afmt = 1, int bfmt = 1) {
   // mode 0: A 128 x K, B N x K.   mode 1: A K(points) x 128, B K(points) x N
   int a_rows = mode == 0 ? 128 : K, a_cols = mode == 0 ? K : 128;
   int b_rows = mode == 0 ? N : K, b_cols = mode == 0 ? K : ((N + 63) / 64) * 64;
@@ -103,8 +109,8 @@ static int run(int mode, int N, int K) {
   for (int r = 0; r < b_rows; ++r)
     for (int c = 0; c < (mode == 0 ? K : N); ++c) B[(size_t)r * b_cols + c] = bf((rand() % 2001 - 1000) / 1000.f);
   std::vector<uint8_t> ai, bi;
-  build_image(A, a_rows, a_cols, ai);
-  build_image(B, b_rows, b_cols, bi);
+  build_image(A, a_rows, a_cols, ai, afmt);
+  build_image(B, b_rows, b_cols, bi, bfmt);
   uint8_t *da, *db;
   float* dc;
   CK(cudaMalloc(&da, ai.size()));
@@ -115,7 +121,7 @@ static int run(int mode, int N, int K) {
   CK(cudaMemset(dc, 0, 128 * N * 4));
   int smem = (int)(((ai.size() + 1023) / 1024) * 1024 + bi.size() + 1024);
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  probe_kernel<<<1, 128, smem>>>(da, (int)ai.size(), db, (int)bi.size(), mode, N, K, a_rows, b_rows, dc);
+  probe_kernel<<<1, 128, smem>>>(da, (int)ai.size(), db, (int)bi.size(), mode, afmt, bfmt, N, K, a_rows, b_rows, dc);
   CK(cudaDeviceSynchronize());
   std::vector<float> C(128 * N);
   CK(cudaMemcpy(C.data(), dc, C.size() * 4, cudaMemcpyDeviceToHost));
@@ -129,7 +135,7 @@ static int run(int mode, int N, int K) {
         for (int p = 0; p < K; ++p) ref += (double)A[(size_t)p * 128 + m] * B[(size_t)p * b_cols + n];
       worst = fmax(worst, fabs(ref - C[m * N + n]));
     }
-  printf("mode %d N %3d K %3d : max abs err %.3e  %s\n", mode, N, K, worst, worst < 1e-3 ? "OK" : "FAIL");
+  printf("mode %d fmt %d%d N %3d K %3d : max abs err %.3e  %s\n", mode, afmt, bfmt, N, K, worst, worst < 1e-3 ? "OK" : "FAIL");
   cudaFree(da);
   cudaFree(db);
   cudaFree(dc);
@@ -146,6 +152,11 @@ int main() {
   bad += run(1, 256, 128);
   bad += run(1, 128, 64);
   bad += run(1, 64, 128);
+  bad += run(0, 256, 256, 0, 0);
+  bad += run(0, 256, 256, 0, 1);
+  bad += run(0, 256, 256, 1, 0);
+  bad += run(1, 256, 128, 0, 1);
+  bad += run(1, 256, 128, 1, 0);
   printf(bad ? "PROBE FAILED (%d)\n" : "PROBE OK\n", bad);
   return bad;
 }
