@@ -17,7 +17,7 @@ RENDER_IDR, RENDER_NERF = 0, 1
 COMP_ABS_DENSITY, COMP_REVERSED, COMP_ZMAX_TAIL = 1, 2, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsvolsdf_b200.so')
+LIB_PATH = os.environ.get('SVS_LIB_PATH') or os.path.join(_HERE, 'libsvolsdf_b200.so')
 
 
 class SvsError(RuntimeError):

@@ -53,7 +53,7 @@ constexpr int kOffVec = kOffStash + kTile * kStashLd * 4;   // 217088 : bias / r
 constexpr int kOffVec2 = kOffVec + 1024;                    // second row vector (256 fp32)
 constexpr int kOffColsum = kOffVec2 + 1024;                 // kMaxColsum x 256 fp32 per-CTA column sums
 constexpr int kOffBar = kOffColsum + kMaxColsum * kColsumW * 4;  // 230656
-constexpr int kSmemBytes = kOffBar + 256;                        // 230912 <= 232448
+constexpr int kSmemBytes = kOffBar + 512;                        // 231168 <= 232448 (227 KB)
 
 enum TcEpi : int32_t {
   EP_SOFTPLUS = 0,  // A' = softplus(acc + b) * scale ; columns >= n_valid: PE(x) * scale (TC_PEFILL) or 0
@@ -197,23 +197,30 @@ constexpr float kSpK1 = 144.26950408889634f;     // 100 * log2(e)
 constexpr float kSpK2 = 0.006931471805599453f;   // ln(2) / 100
 constexpr float kSpThr = 28.853900817779268f;    // 20 * log2(e): Softplus threshold (network.py:69, torch default 20)
 // Softplus(beta=100, threshold 20) * scale with one ex2 + one lg2 (abs. error of the lg2(1+e) form <= 1e-9)
-__device__ __forceinline__ float softplus100_fast(float z, float scale) {
+// c_lo = ln2/100 * scale, c_hi = scale / (100 log2 e).  softplus(z) >= z, and the capped branch stays at softplus(0.2),
+// so max() selects z exactly where torch's threshold does.
+__device__ __forceinline__ float softplus100_fast(float z, float c_lo, float c_hi) {
+#ifdef SVS_DBG_NOMUFU
+  return fmaxf(z * c_lo, z * c_hi);
+#endif
   float t = z * kSpK1;
   float l = lg2_approx(1.0f + ex2_approx(fminf(t, kSpThr)));
-  return (t > kSpThr) ? z * scale : l * (kSpK2 * scale);
+  return fmaxf(l * c_lo, t * c_hi);
 }
 // sigma'(z) recovered from h = softplus(z): 1 - exp(-100 h)
 __device__ __forceinline__ float dsoftplus_h(float h) { return 1.0f - ex2_approx(-kSpK1 * h); }
 
 __device__ __forceinline__ float pe_col(const float (&xv)[4], int d_in, int n_freqs, int c) {
   if (c < d_in) return xv[c];
+
   int t = c - d_in;
   int k = t / (2 * d_in);
   if (k >= n_freqs) return 0.f;
   int rem = t - k * 2 * d_in;
   int fn = rem / d_in, dim = rem - fn * d_in;
+  // MUFU sin/cos: |arg| <= 2^(n_freqs-1) * |x| ~ 1e2 -> abs. error ~1e-5, far below the fp16 operand rounding (5e-4)
   float arg = xv[dim] * (float)(1 << k);
-  return fn ? cosf(arg) : sinf(arg);
+  return fn ? __cosf(arg) : __sinf(arg);
 }
 // d PE_c / d x_dim(c)
 __device__ __forceinline__ float pe_dcol(const float (&xv)[4], int d_in, int n_freqs, int c, int* dim_out) {
@@ -226,7 +233,7 @@ __device__ __forceinline__ float pe_dcol(const float (&xv)[4], int d_in, int n_f
   float f = (float)(1 << k);
   float arg = xv[dim] * f;
   *dim_out = dim;
-  return fn ? (-f * sinf(arg)) : (f * cosf(arg));
+  return fn ? (-f * __sinf(arg)) : (f * __cosf(arg));
 }
 
 __device__ __forceinline__ float clamp_w(float y0, float sphere) { return (y0 < sphere) ? 1.f : ((y0 == sphere) ? 0.5f : 0.f); }
@@ -246,8 +253,9 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-struct Bars {
-  uint64_t w_full[kWSlots], w_empty[kWSlots], x_full[kXSlots], x_empty[kXSlots], a_ready[kMaxKB], acc_full, a_load;
+struct Bars {   // must fit the 512 bytes reserved at kOffBar
+  uint64_t w_full[kWSlots], w_empty[kWSlots], x_full[kXSlots], x_empty[kXSlots], a_ready[kMaxKB * 4], s_free[kMaxKB], acc_full,
+      a_load;
   uint32_t tmem;
 };
 
@@ -263,7 +271,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
   uint8_t* sW = smem + kOffW;
   uint8_t* sX = smem + kOffX;
   float* stash = reinterpret_cast<float*>(smem + kOffStash);
-  float* vec = reinterpret_cast<float*>(smem + kOffVec);
   float* colsum = reinterpret_cast<float*>(smem + kOffColsum);
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBar);
 
@@ -272,7 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWSlots; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < kXSlots; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kEpiWarps); }
-    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->a_ready[i], kEpiWarps);
+    for (int i = 0; i < kMaxKB * 4; ++i) mbar_init(&bars->a_ready[i], kEpiWarps / 4);   // one per 16-column quarter
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->s_free[i], 1);
     mbar_init(&bars->acc_full, 1);
     mbar_init(&bars->a_load, 1);
     mbar_fence_init();
@@ -312,20 +320,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
           const uint32_t acc = tmem + (n_step & 1) * 256;
           for (int kb = 0; kb < st.KB; ++kb, ++seq) {
-            mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
-            a_par ^= 1u << kb;
             const int slot = seq % kWSlots;
             const uint32_t use = seq / kWSlots;
             mbar_wait(&bars->w_full[slot], use & 1);
-            tc_fence_after();
             const uint32_t a0 = smem_u32(sA + kb * kBlk), b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j) {
+              // k-step j multiplies columns [64 kb + 16 j, +16): exactly what the 4 epilogue warps with cq == j wrote
+              const int bi = kb * 4 + j;
+              mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
+              a_par ^= 1u << bi;
+              tc_fence_after();
               umma_f16(acc, make_smem_desc(a0 + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc,
                        (kb | j) != 0);
+            }
             umma_commit(&bars->w_empty[slot]);
           }
           umma_commit(&bars->acc_full);
+        }
+        // a last step that rewrites A publishes blocks nobody multiplies: consume their phases
+        const int tail_kb = ch.st[ch.n_steps - 1].next_kb;
+        for (int bi = 0; bi < tail_kb * 4; ++bi) {
+          mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
+          a_par ^= 1u << bi;
         }
       }
     }
@@ -354,6 +371,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         }
       }
     }
+  } else if (warp == 3) {
+    // ===== store warp: saves every generation of the A tile (bulk store straight from smem) and hands the blocks
+    //       back to the epilogue (s_free) once the async proxy has read them =====
+    if (lane == 0) {
+      uint32_t a_par = 0;
+      auto consume = [&](int kb) {
+        for (int bi = kb * 4; bi < kb * 4 + 4; ++bi) {
+          mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
+          a_par ^= 1u << bi;
+        }
+      };
+      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        for (int b = 0; b < ch.pro_kb; ++b) consume(b);
+        if (ch.pro_save >= 0) {
+          bulk_s2g(ch.img[ch.pro_save].base + (size_t)t * ch.img[ch.pro_save].tile_bytes, sA, (uint32_t)ch.pro_kb * kBlk);
+          bulk_commit();
+          bulk_wait_read<0>();
+        }
+        for (int b = 0; b < ch.pro_kb; ++b) mbar_arrive(&bars->s_free[b]);
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          if (st.next_kb > 0) {
+            for (int c = 0; c < st.next_kb; ++c) {
+              consume(c);
+              if (st.save >= 0) {
+                bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes + (size_t)c * kBlk, sA + c * kBlk, kBlk);
+                bulk_commit();
+              }
+            }
+            if (st.save >= 0) bulk_wait_read<0>();
+            for (int c = 0; c < st.next_kb; ++c) mbar_arrive(&bars->s_free[c]);
+          } else if (s + 1 < ch.n_steps) {
+            for (int c = 0; c < ch.st[s + 1].KB; ++c) consume(c);
+          }
+        }
+      }
+      bulk_wait_all<0>();
+    }
   } else if (warp >= 4) {
     // ===== epilogue warps =====
     const int ew = warp - 4, q = ew & 3, cq = ew >> 2;
@@ -361,11 +416,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     const int et = threadIdx.x - 128;
     const bool leader = (et == 0);
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t n_acc = 0, xseq = 0, n_load = 0;
+    uint32_t n_acc = 0, xseq = 0, n_load = 0, fgen = 0;   // fgen: parity of the write generation of each A block
     const float gs = grad_scale(ch.amax, ch.amax_target);
     const float inv_gs = 1.0f / gs;
     const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
     const bool clamp_on = ch.clamp && ch.radius > 0.f;
+    // biases of all steps live in shared memory for the whole kernel (the stash region is free in the chains that
+    // have biases: forward SDF / rendering nets)
+    constexpr bool kHasBias = (EPI & (epi_bit(EP_SOFTPLUS) | epi_bit(EP_SDF) | epi_bit(EP_Y) | epi_bit(EP_RELU) | epi_bit(EP_RGB))) != 0;
+    static_assert(!kHasBias || (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD))) == 0, "bias table shares the stash region");
+    static_assert(kMaxSteps * 256 * 4 <= kTile * kStashLd * 4, "bias table must fit the stash region");
+    float* btab = stash;
+    if (kHasBias) {
+      for (int s = 0; s < ch.n_steps; ++s) {
+        const float* b = ch.st[s].bias;
+        const int nv = ch.st[s].n_valid;
+        if (et < 256) btab[s * 256 + et] = (b && et < nv) ? b[et] : 0.f;
+      }
+      named_bar_sync(1, kEpiThreads);
+    }
 
     for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
       const int64_t p = (int64_t)t * kTile + m;
@@ -385,13 +454,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
       float dg[4] = {0.f, 0.f, 0.f, 0.f};  // grad_scale * w * dL/dgrad of the point (tangent sweep)
       if (PRO == PRO_PE_JVP && ch.d_grad && live)
         for (int d = 0; d < ch.d_in; ++d) dg[d] = gs * cw * ch.d_grad[p * ch.d_in + d];
-      // the previous tile's last save must have left the A tile before the prologue overwrites it
-      if (leader) bulk_wait_read<0>();
       if (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD)))
         for (int i = cq; i < kStashLd; i += 4) stash[m * kStashLd + i] = 0.f;
       if (PRO == PRO_LOAD_ULAST) {
-        if (et < 256) vec[et] = ch.pro_vec[et];
         if (leader) {
+          // the blocks must have been saved (previous tile) before the async proxy overwrites them
+          for (int b = 0; b < ch.pro_kb; ++b) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
           const uint32_t bytes = (uint32_t)ch.pro_kb * kBlk;
           mbar_arrive_expect_tx(&bars->a_load, bytes);
           bulk_g2s(sA, ch.img[ch.pro_img].base + (size_t)t * ch.img[ch.pro_img].tile_bytes, bytes, &bars->a_load);
@@ -413,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         } else if (PRO == PRO_LOAD_ULAST) {
           ld_row16(sA + b * kBlk, m, cq, v);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = dsoftplus_h(v[i]) * vec[c0 + i];
+          for (int i = 0; i < 16; ++i) v[i] = dsoftplus_h(v[i]) * __ldg(ch.pro_vec + c0 + i);
         } else if (PRO == PRO_RENDER_IN) {
           const int nfb = ch.F >> 6;  // feature blocks, then one block [points(3) if idr, PE(view), normals(3) if idr]
           if (b < nfb) {
@@ -481,6 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             v[i] = r;
           }
         }
+        mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
+        fgen ^= 1u << b;
         st_row16(sA + b * kBlk, m, cq, v);
         if (ch.pro_colsum >= 0) {
           float cs = warp_colsum16(v, lane);
@@ -488,48 +558,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->a_ready[b]);
-      }
-      named_bar_sync(1, kEpiThreads);
-      if (leader && ch.pro_save >= 0) {
-        bulk_s2g(ch.img[ch.pro_save].base + (size_t)t * ch.img[ch.pro_save].tile_bytes, sA, (uint32_t)ch.pro_kb * kBlk);
-        bulk_commit();
+        if (lane == 0) mbar_arrive(&bars->a_ready[b * 4 + cq]);
       }
 
       // ---------------- steps ----------------
       for (int s = 0; s < ch.n_steps; ++s) {
-        const TcStep& st = ch.st[s];
+        const TcStep st = ch.st[s];   // by value: keeps the hot fields in registers instead of indexed constant loads
+        const float* btab_s = btab + s * 256;
         const bool has_next = s + 1 < ch.n_steps;
         const bool writes_a = st.next_kb > 0;
-        // stage the step's bias, wait for the accumulator, make sure the last save has left the A tile
-        if (st.bias && et < 256) vec[et] = (et < st.n_valid) ? st.bias[et] : 0.f;
+        const float c_lo = kSpK2 * st.scale, c_hi = st.scale / kSpK1;
         const uint32_t tm_acc = tm_row + (n_acc & 1) * 256;
         mbar_wait(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
-        if (leader) bulk_wait_read<0>();
-        named_bar_sync(1, kEpiThreads);
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
-            for (int c = 0; c < ch.st[s + 1].KB; ++c) mbar_arrive(&bars->a_ready[c]);
+            for (int c = 0; c < ch.st[s + 1].KB; ++c) mbar_arrive(&bars->a_ready[c * 4 + cq]);
         }
 
         const int nchunk_acc = (st.n_pad + 63) >> 6;
         const int nchunk = max(nchunk_acc, st.next_kb);
+        uint32_t rr[16];   // accumulator columns of the NEXT chunk (tcgen05.ld issued one chunk ahead)
+        if (cq * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(cq * 16), rr);
         for (int c = 0; c < nchunk; ++c) {
           const int col0 = c * 64 + cq * 16;
           float acc[16];
           if (col0 < st.n_pad) {
-            uint32_t r[16];
-            tmem_ld_32x16(tm_acc + (uint32_t)col0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rr[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
           }
+          if (col0 + 64 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + 64), rr);
           // aux tiles of this chunk
           float a1[16], a2[16];
           int slot1 = -1, slot2 = -1;
@@ -553,28 +617,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           const bool full = col0 + 16 <= st.n_valid;   // no pad columns in this thread's 16
           if ((EPI & epi_bit(EP_SOFTPLUS)) && st.epi == EP_SOFTPLUS) {
             if (full) {
-              const float4* b4 = reinterpret_cast<const float4*>(vec + col0);
+              const float4* b4 = reinterpret_cast<const float4*>(btab_s + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                float4 b = b4[i];
-                o[4 * i + 0] = softplus100_fast(acc[4 * i + 0] + b.x, st.scale);
-                o[4 * i + 1] = softplus100_fast(acc[4 * i + 1] + b.y, st.scale);
-                o[4 * i + 2] = softplus100_fast(acc[4 * i + 2] + b.z, st.scale);
-                o[4 * i + 3] = softplus100_fast(acc[4 * i + 3] + b.w, st.scale);
+                const float4 b = b4[i];
+                o[4 * i + 0] = softplus100_fast(acc[4 * i + 0] + b.x, c_lo, c_hi);
+                o[4 * i + 1] = softplus100_fast(acc[4 * i + 1] + b.y, c_lo, c_hi);
+                o[4 * i + 2] = softplus100_fast(acc[4 * i + 2] + b.z, c_lo, c_hi);
+                o[4 * i + 3] = softplus100_fast(acc[4 * i + 3] + b.w, c_lo, c_hi);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int n = col0 + i;
                 float r = 0.f;
-                if (n < st.n_valid) r = softplus100_fast(acc[i] + vec[n & 255], st.scale);
+                if (n < st.n_valid) r = softplus100_fast(acc[i] + btab_s[n & 255], c_lo, c_hi);
                 else if (st.flags & TC_PEFILL) r = pe_col(xv, ch.d_in, ch.n_freqs, n - st.n_valid) * st.scale;
                 o[i] = r;
               }
             }
           } else if ((EPI & epi_bit(EP_SDF)) && st.epi == EP_SDF) {
             if (col0 == 0 && live) {
-              float y0 = acc[0] + vec[0];
+              float y0 = acc[0] + btab_s[0];
               if (clamp_on) y0 = fminf(y0, sphere);
               ch.sdf[p] = y0;
             }
@@ -583,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
               float* dst = ch.y + p * ch.ldy + st.y_col + col0;
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                if (col0 + i < st.n_valid) dst[i] = acc[i] + vec[(col0 + i) & 255];
+                if (col0 + i < st.n_valid) dst[i] = acc[i] + btab_s[(col0 + i) & 255];
             }
           } else if ((EPI & epi_bit(EP_REVERSE)) && st.epi == EP_REVERSE) {
 #pragma unroll
@@ -603,14 +667,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int n = col0 + i;
-              o[i] = (n < st.n_valid) ? fmaxf(acc[i] + vec[n & 255], 0.f) : 0.f;
+              o[i] = (n < st.n_valid) ? fmaxf(acc[i] + btab_s[n & 255], 0.f) : 0.f;
             }
           } else if ((EPI & epi_bit(EP_RGB)) && st.epi == EP_RGB) {
             if (live) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int n = col0 + i;
-                if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + __expf(-(acc[i] + vec[n & 255])));
+                if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + __expf(-(acc[i] + btab_s[n & 255])));
               }
             }
           } else if ((EPI & epi_bit(EP_RELU_BWD)) && st.epi == EP_RELU_BWD) {
@@ -662,11 +726,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             }
           }
           if (writes_a && c < st.next_kb) {
+            mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
+            fgen ^= 1u << c;
+#ifndef SVS_DBG_NOSTORE
             st_row16(sA + c * kBlk, m, cq, o);
+#endif
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0 && has_next) mbar_arrive(&bars->a_ready[c]);
+            if (lane == 0) mbar_arrive(&bars->a_ready[c * 4 + cq]);
             if (st.colsum >= 0) {
               float cs = warp_colsum16(o, lane);
               if (lane < 16) atomicAdd(&colsum[st.colsum * kColsumW + col0 + lane], cs);
@@ -714,16 +782,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             if (ch.grad)
               for (int d = 0; d < ch.d_in; ++d) ch.grad[p * ch.d_in + d] = g[d];
           }
+          named_bar_sync(2, kEpiThreads);   // the stash is re-zeroed by the next tile's prologue
         }
         tc_fence_before();
-        named_bar_sync(1, kEpiThreads);
-        if (leader && st.save >= 0) {
-          bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes, sA, (uint32_t)st.next_kb * kBlk);
-          bulk_commit();
-        }
       }
     }
-    if (leader) bulk_wait_all<0>();
+    if (leader) bulk_wait_all<0>();   // zeta stores of the tangent chain
     // flush the per-CTA column sums (bias gradients, dW_last[0,:])
     named_bar_sync(1, kEpiThreads);
     for (int k = 0; k < kMaxColsum; ++k) {
@@ -735,6 +799,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
+
+static_assert(sizeof(Bars) <= 512, "barrier block overflows its shared-memory reservation");
 
 constexpr uint32_t kEpiFwd = epi_bit(EP_SOFTPLUS) | epi_bit(EP_SDF) | epi_bit(EP_Y);
 constexpr uint32_t kEpiRev = epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD);
