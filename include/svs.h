@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define SVS_MAX_LAYERS 12
-#define SVS_ABI_VERSION 2
+#define SVS_ABI_VERSION 3
 
 typedef enum {
   SVS_OK = 0,
@@ -99,7 +99,9 @@ int svs_mlp_param_grads(const svs_mlp_desc* d, const svs_mlp_params* p, const fl
  *                             get_sdf_vals() (network.py:125-131): sdf (P) with the sphere clamp.
  *   svs_sdf_outputs_forward = get_outputs()/gradient() (network.py:90-123): raw outputs y (P, ldy),
  *                             clamped sdf (P), analytic d sdf/dx (P, d_in); `saved` (optional) receives the
- *                             activations the backward needs (svs_sdf_saved_floats).  clamp=0 gives gradient().
+ *                             activations the backward needs (svs_sdf_saved_floats).  Points [0, n_clamped) take the
+ *                             sphere clamp (get_outputs), points [n_clamped, P) do not (gradient(): the eikonal
+ *                             samples ride in the same launch as the ray samples).
  *   svs_sdf_outputs_backward= autograd backward + double-backward of the above (loss.backward() through
  *                             network.py:105-123): dy (P, ldy) = dL/d raw outputs (col 0 is combined with
  *                             d_sdf through the clamp), d_sdf (P) optional, d_grad (P, d_in) optional;
@@ -111,10 +113,10 @@ int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad, int e
 int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P, int engine);
 int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, float* y,
                     float* sdf, float* ws, int engine, void* stream);
-int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
+int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int64_t n_clamped,
                             float* y, float* sdf, float* grad, float* saved, float* ws, int engine,
                             void* stream);
-int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
+int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int64_t n_clamped,
                              const float* saved, const float* y, const float* dy, const float* d_sdf,
                              const float* d_grad, float* dwbuf, float* ws, int engine, void* stream);
 int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P, int engine);

@@ -60,8 +60,8 @@ SIGNATURES = {
     'svs_sdf_saved_floats': (_I64, [_DESC, _I64, C.c_int]),
     'svs_sdf_bwd_ws_floats': (_I64, [_DESC, _I64, C.c_int]),
     'svs_sdf_forward': (C.c_int, [_DESC, _P, _P, _I64, _P, _P, _P, C.c_int, _P]),
-    'svs_sdf_outputs_forward': (C.c_int, [_DESC, _P, _P, _I64, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
-    'svs_sdf_outputs_backward': (C.c_int, [_DESC, _P, _P, _I64, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    'svs_sdf_outputs_forward': (C.c_int, [_DESC, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, C.c_int, _P]),
+    'svs_sdf_outputs_backward': (C.c_int, [_DESC, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     'svs_embed': (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     'svs_render_saved_floats': (_I64, [_DESC, _I64, C.c_int]),
     'svs_render_ws_floats': (_I64, [_DESC, _I64, C.c_int]),

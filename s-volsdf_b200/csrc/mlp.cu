@@ -199,7 +199,7 @@ __device__ __forceinline__ float clamp_factor(float y0, float sphere, bool clamp
 // g = J_PE(x)^T (p0 + e), sphere clamp of sdf and g (network.py:105-123,125-131)
 __global__ void pe_grad_kernel(const float* __restrict__ x, const float* __restrict__ P0, const float* __restrict__ E,
                                int ld0, const float* __restrict__ y, int ldy, int64_t P, int d_in, int n_freqs,
-                               float radius, float sph_scale, int clamp, float* __restrict__ sdf,
+                               float radius, float sph_scale, long long n_clamp, float* __restrict__ sdf,
                                float* __restrict__ grad) {
   int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (m >= P) return;
@@ -226,7 +226,7 @@ __global__ void pe_grad_kernel(const float* __restrict__ x, const float* __restr
   }
   float y0 = y[m * ldy];
   float out_sdf = y0;
-  if (clamp && radius > 0.f) {
+  if (m < n_clamp && radius > 0.f) {
     float nrm = sqrtf(nrm2);
     float sphere = sph_scale * (radius - nrm);
     float w = clamp_factor(y0, sphere, true);
@@ -240,11 +240,11 @@ __global__ void pe_grad_kernel(const float* __restrict__ x, const float* __restr
 
 // sdf[m] = clamp(y[m,0])  (get_sdf_vals, network.py:125-131)
 __global__ void sdf_clamp_kernel(const float* __restrict__ x, const float* __restrict__ y, int ldy, int64_t P, int d_in,
-                                 float radius, float sph_scale, float* __restrict__ sdf) {
+                                 float radius, float sph_scale, long long n_clamp, float* __restrict__ sdf) {
   int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (m >= P) return;
   float y0 = y[m * ldy];
-  if (radius > 0.f) {
+  if (m < n_clamp && radius > 0.f) {
     float n2 = 0.f;
     for (int d = 0; d < d_in; ++d) n2 += x[m * d_in + d] * x[m * d_in + d];
     y0 = fminf(y0, sph_scale * (radius - sqrtf(n2)));
@@ -254,7 +254,7 @@ __global__ void sdf_clamp_kernel(const float* __restrict__ x, const float* __res
 
 // Q0 = J_PE(x) (w * d_grad) written at dst[m, col_off + c]*scale; w = clamp factor of the point
 __global__ void pe_jvp_kernel(const float* __restrict__ x, const float* __restrict__ d_grad, const float* __restrict__ y,
-                              int ldy, int64_t P, int d_in, int n_freqs, float radius, float sph_scale, int clamp,
+                              int ldy, int64_t P, int d_in, int n_freqs, float radius, float sph_scale, long long n_clamp,
                               float* __restrict__ dst, int ld, int col_off, float scale, int pad_to) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t m = idx / pad_to;
@@ -262,7 +262,7 @@ __global__ void pe_jvp_kernel(const float* __restrict__ x, const float* __restri
   if (m >= P) return;
   int pe_w = d_in * (1 + 2 * n_freqs);
   float w = 1.f;
-  if (clamp && radius > 0.f) {
+  if (m < n_clamp && radius > 0.f) {
     float n2 = 0.f;
     for (int d = 0; d < d_in; ++d) n2 += x[m * d_in + d] * x[m * d_in + d];
     w = clamp_factor(y[m * ldy], sph_scale * (radius - sqrtf(n2)), true);
@@ -296,7 +296,7 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, int64_t
 // DY[m,c] = dy[m,c] (or 0) ; column 0 additionally receives w * d_sdf[m]
 __global__ void dy_prep_kernel(const float* __restrict__ dy, const float* __restrict__ d_sdf, const float* __restrict__ x,
                                const float* __restrict__ y, int ldy, int64_t P, int n_out, int d_in, float radius,
-                               float sph_scale, int clamp, float* __restrict__ DY) {
+                               float sph_scale, long long n_clamp, float* __restrict__ DY) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t m = idx / ldy;
   int c = (int)(idx - m * ldy);
@@ -304,7 +304,7 @@ __global__ void dy_prep_kernel(const float* __restrict__ dy, const float* __rest
   float v = (dy && c < n_out) ? dy[m * ldy + c] : 0.f;
   if (c == 0 && d_sdf) {
     float w = 1.f;
-    if (clamp && radius > 0.f) {
+    if (m < n_clamp && radius > 0.f) {
       float n2 = 0.f;
       for (int d = 0; d < d_in; ++d) n2 += x[m * d_in + d] * x[m * d_in + d];
       w = clamp_factor(y[m * ldy], sph_scale * (radius - sqrtf(n2)), true);
@@ -532,7 +532,7 @@ extern "C" int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const f
     SVS_TRY((launch_gemm<true, EPI_BIAS>(g, st)));
   }
   if (sdf) {
-    sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, Y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale, sdf);
+    sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, Y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale, P, sdf);
     SVS_LAUNCH_OK();
   }
   return SVS_OK;
@@ -550,7 +550,7 @@ static void map_saved(const Layout& lo, int64_t P, float* base, SdfBuffers* b) {
   for (int l = 0; l < lo.L - 1; ++l, p += P * lo.H) b->U[l] = p;
 }
 
-extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
+extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int64_t n_clamped,
                                        float* y, float* sdf, float* grad, float* saved, float* ws, int engine,
                                        void* stream) {
   Layout lo;
@@ -563,13 +563,13 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
     if (!grad && !saved) {
       SVS_TRY(tc::sdf_forward(d, lo, wbuf, x, P, y, nullptr, st));
       if (sdf) {
-        sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, clamp ? d->sphere_radius : 0.f,
-                                                        d->sphere_scale, sdf);
+        sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale,
+                                                        n_clamped, sdf);
         SVS_LAUNCH_OK();
       }
       return SVS_OK;
     }
-    return tc::sdf_outputs_forward(d, lo, wbuf, x, P, clamp, y, sdf, grad, saved ? (void*)saved : (void*)ws, st);
+    return tc::sdf_outputs_forward(d, lo, wbuf, x, P, n_clamped, y, sdf, grad, saved ? (void*)saved : (void*)ws, st);
   }
   SdfBuffers b;
   float* scratch = ws;
@@ -612,8 +612,8 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
   }
   if (!grad && !saved) {
     if (sdf) {
-      sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, clamp ? d->sphere_radius : 0.f,
-                                                      d->sphere_scale, sdf);
+      sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale,
+                                                      n_clamped, sdf);
       SVS_LAUNCH_OK();
     }
     return SVS_OK;
@@ -644,12 +644,12 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
     SVS_TRY((launch_gemm<false, EPI_PLAIN>(g, st)));
   }
   pe_grad_kernel<<<blocks_for(P), 256, 0, st>>>(x, P0, lo.skip > 0 ? E : nullptr, lo.ld0, y, lo.ldy, P, d->d_in,
-                                                d->n_freqs, d->sphere_radius, d->sphere_scale, clamp, sdf, grad);
+                                                d->n_freqs, d->sphere_radius, d->sphere_scale, n_clamped, sdf, grad);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }
 
-extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int clamp,
+extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf, const float* x, int64_t P, int64_t n_clamped,
                                         const float* saved, const float* y, const float* dy, const float* d_sdf,
                                         const float* d_grad, float* dwbuf, float* ws, int engine, void* stream) {
   Layout lo;
@@ -659,7 +659,7 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == SVS_ENGINE_TC)
-    return tc::sdf_outputs_backward(d, lo, wbuf, x, P, clamp, saved, y, dy, d_sdf, d_grad, dwbuf, ws, st);
+    return tc::sdf_outputs_backward(d, lo, wbuf, x, P, n_clamped, saved, y, dy, d_sdf, d_grad, dwbuf, ws, st);
   const int L = lo.L;
   SdfBuffers b;
   map_saved(lo, P, const_cast<float*>(saved), &b);
@@ -673,12 +673,12 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
   const bool have_tangent = d_grad != nullptr;
   const bool have_top = (dy != nullptr) || (d_sdf != nullptr);
   if (!have_tangent && !have_top) return SVS_OK;
-  const float radius = clamp ? d->sphere_radius : 0.f;
+  const float radius = d->sphere_radius;
 
   // ---- tangent sweep (adjoint of the reverse sweep): q_{l+1} = s_l * (W_l q_l), zeta_l, dW_l += U_l^T q_l ----
   if (have_tangent) {
     pe_jvp_kernel<<<blocks_for(P * lo.ld0), 256, 0, st>>>(x, d_grad, y, lo.ldy, P, d->d_in, d->n_freqs, radius,
-                                                          d->sphere_scale, clamp, Q0, lo.ld0, 0, 1.f, lo.ld0);
+                                                          d->sphere_scale, n_clamped, Q0, lo.ld0, 0, 1.f, lo.ld0);
     SVS_LAUNCH_OK();
     const float* q_in = Q0;
     int ld_q = lo.ld0;
@@ -712,7 +712,7 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
   int cur = 0;
   if (have_top) {
     dy_prep_kernel<<<blocks_for(P * lo.ldy), 256, 0, st>>>(dy, d_sdf, x, y, lo.ldy, P, lo.out[L - 1], d->d_in, radius,
-                                                           d->sphere_scale, clamp, DY);
+                                                           d->sphere_scale, n_clamped, DY);
     SVS_LAUNCH_OK();
     int l = L - 1;
     SVS_TRY(launch_gemm_tn(DY, lo.ldy, b.A[l], lo.H, dwbuf + lo.woff[l], lo.ldi[l], P, lo.out[l], lo.ldi[l], st));

@@ -115,7 +115,7 @@ struct TcChain {
   const float* x;
   int32_t d_in, n_freqs;
   float radius, sph_scale;
-  int32_t clamp;
+  int64_t n_clamped;           // points [0, n_clamped) take the bounding-sphere minimum (get_outputs), the rest do not (gradient)
   // fp32 inputs / outputs (row-major)
   float* y; int32_t ldy;
   const float* yin;            // raw sdf column source for the clamp (reverse / tangent / backward chains)
@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     const float gs = grad_scale(ch.amax, ch.amax_target);
     const float inv_gs = 1.0f / gs;
     const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
-    const bool clamp_on = ch.clamp && ch.radius > 0.f;
     // biases of all steps live in shared memory for the whole kernel (the stash region is free in the chains that
     // have biases: forward SDF / rendering nets)
     constexpr bool kHasBias = (EPI & (epi_bit(EP_SOFTPLUS) | epi_bit(EP_SDF) | epi_bit(EP_Y) | epi_bit(EP_RELU) | epi_bit(EP_RGB))) != 0;
@@ -444,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         for (int d = 0; d < ch.d_in; ++d) xv[d] = ch.x[p * ch.d_in + d];
       // sphere clamp of the point (get_outputs / get_sdf_vals, network.py:108-112,128-130)
       float sphere = 0.f, cw = 1.f, nrm = 1.f;
+      const bool clamp_on = ch.radius > 0.f && p < ch.n_clamped;
       if (clamp_on) {
         float n2 = 0.f;
         for (int d = 0; d < ch.d_in; ++d) n2 += xv[d] * xv[d];

@@ -5,14 +5,14 @@
 namespace svs {
 namespace tc {
 
-static void sdf_geometry(TcChain* ch, const svs_mlp_desc* d, const float* x, int64_t P, int clamp) {
+static void sdf_geometry(TcChain* ch, const svs_mlp_desc* d, const float* x, int64_t P, int64_t n_clamped) {
   ch->P = P;
   ch->x = x;
   ch->d_in = d->d_in;
   ch->n_freqs = d->n_freqs;
   ch->radius = d->sphere_radius;
   ch->sph_scale = d->sphere_scale;
-  ch->clamp = clamp;
+  ch->n_clamped = n_clamped;
 }
 
 // forward layers 0..L-2 (softplus); saves h_{l+1} when `sv` is given
@@ -48,7 +48,7 @@ static int sdf_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbu
   const int L = lo.L;
   TcChain ch;
   init_chain(&ch);
-  sdf_geometry(&ch, d, x, P, 1);
+  sdf_geometry(&ch, d, x, P, P);
   add_sdf_forward_steps(&ch, lo, wi, wbuf, nullptr);
   ch.y = y;
   ch.ldy = lo.ldy;
@@ -68,14 +68,14 @@ static int sdf_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbu
 
 // get_outputs()/gradient(): y, clamped sdf, d sdf/dx; `saved` keeps A0, h_1..h_{L-1}, U_0..U_{L-2} for the backward
 static int sdf_outputs_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbuf, const float* x, int64_t P,
-                               int clamp, float* y, float* sdf, float* grad, void* saved, cudaStream_t st) {
+                               int64_t clamp, float* y, float* sdf, float* grad, void* saved, cudaStream_t st) {
   WImages wi;
   SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr));
   const uint8_t* reg = wimg_region(lo, wbuf);
   const int L = lo.L;
   SdfSaved sv;
   map_sdf_saved(lo, P, saved, &sv);
-  SVS_CHECK_ARG(lo.pe_w <= kStashLd, "tcgen05 engine: analytic gradient supports PE widths up to %d (got %d)", kStashLd, lo.pe_w);
+  SVS_CHECK_ARG(!grad || lo.pe_w <= kStashLd, "tcgen05 engine: analytic gradient supports PE widths up to %d (got %d)", kStashLd, lo.pe_w);
   {
     TcChain ch;
     init_chain(&ch);
@@ -88,6 +88,15 @@ static int sdf_outputs_forward(const svs_mlp_desc* d, const Layout& lo, const fl
     s1.y_col = 1;
     ch.st[ch.n_steps++] = s1;
     SVS_TRY(launch_chain(ch, "mlp_tc_sdf_fwd", chain_flops(ch), 0.0, st));
+  }
+  if (!grad) {
+    // no analytic gradient wanted (e.g. the background SDF net): the backward then has no tangent sweep and never
+    // reads U, so the reverse sweep is skipped; only the clamped sdf remains to be produced
+    if (sdf) {
+      sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale, clamp, sdf);
+      SVS_LAUNCH_OK();
+    }
+    return SVS_OK;
   }
   {
     // reverse sweep: p_l = W_l^T (s_l * p_{l+1}), kept as U_l = s_l * p~_{l+1}
@@ -128,7 +137,7 @@ static int sdf_outputs_forward(const svs_mlp_desc* d, const Layout& lo, const fl
 }
 
 static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const float* wbuf, const float* x, int64_t P,
-                                int clamp, const void* saved, const float* y, const float* dy, const float* d_sdf,
+                                int64_t clamp, const void* saved, const float* y, const float* dy, const float* d_sdf,
                                 const float* d_grad, float* dwbuf, void* ws, cudaStream_t st) {
   WImages wi;
   SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr));

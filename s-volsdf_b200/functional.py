@@ -91,6 +91,8 @@ def sdf_forward_nograd(net, x, want_y, want_sdf):
 
 class SdfOutputsFn(torch.autograd.Function):
     """x (P,d_in) -> y (P,ldy) raw outputs, sdf (P,1) clamped, grad (P,d_in) = d sdf / d x.
+    `clamp`: True / False, or an int n: only the first n points take the bounding-sphere minimum (the ray samples of
+    get_outputs(); the eikonal samples of gradient() ride behind them in the same launch).
 
     backward implements loss.backward() through get_outputs()/gradient(): first-order terms through y/sdf
     and the double-backward through the analytic gradient."""
@@ -104,12 +106,13 @@ class SdfOutputsFn(torch.autograd.Function):
         lib = L.load()
         y = _f32(P, net.ldy, device=dev)
         sdf = _f32(P, 1, device=dev)
-        grad = _f32(P, net.desc.d_in, device=dev) if (want_grad or train) else None
+        grad = _f32(P, net.desc.d_in, device=dev) if want_grad else None
         saved = _f32(max(1, int(lib.svs_sdf_saved_floats(net.desc, P, net.engine))), device=dev) if train else None
         ws = _f32(max(1, int(lib.svs_sdf_ws_floats(net.desc, P, 0 if train else 1, net.engine))), device=dev)
-        L.call('svs_sdf_outputs_forward', net.desc, ptr(wbuf), ptr(x), P, 1 if clamp else 0, ptr(y), ptr(sdf),
+        n_clamped = P if clamp is True else (0 if not clamp else int(clamp))   # True: all points, int: the leading n
+        L.call('svs_sdf_outputs_forward', net.desc, ptr(wbuf), ptr(x), P, n_clamped, ptr(y), ptr(sdf),
                ptr(grad), ptr(saved), ptr(ws), net.engine, L.stream())
-        ctx.net, ctx.clamp, ctx.P = net, clamp, P
+        ctx.net, ctx.clamp, ctx.P = net, n_clamped, P
         if train:
             ctx.save_for_backward(x, y, saved, wbuf)
         if grad is None:
@@ -126,7 +129,7 @@ class SdfOutputsFn(torch.autograd.Function):
         dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
         ws = _f32(max(1, int(lib.svs_sdf_bwd_ws_floats(net.desc, P, net.engine))), device=dev)
         dy, d_sdf, d_grad = _contig(dy), _contig(d_sdf), _contig(d_grad)
-        L.call('svs_sdf_outputs_backward', net.desc, ptr(wbuf), ptr(x), P, 1 if ctx.clamp else 0, ptr(saved), ptr(y),
+        L.call('svs_sdf_outputs_backward', net.desc, ptr(wbuf), ptr(x), P, ctx.clamp, ptr(saved), ptr(y),
                ptr(dy), ptr(d_sdf), ptr(d_grad), ptr(dwbuf), ptr(ws), net.engine, L.stream())
         grads = net.param_grads(wbuf, dwbuf)
         return (None, None, None, None, None) + tuple(grads)

@@ -217,7 +217,17 @@ class VolSDFNetwork(nn.Module):
         points_flat = points.reshape(-1, 3)
         dirs_flat = ray_dirs.unsqueeze(1).expand(R, S, 3).reshape(-1, 3)
 
-        y, sdf, gradients = self.implicit_network.outputs_fused(points_flat, clamp=True)
+        n_main = points_flat.shape[0]
+        if self.training:
+            # eikonal samples (network.py:258-268): R uniform points in the bounding box + one near-surface point per
+            # ray.  They go through the SDF net in the SAME launches as the ray samples (unclamped tail of the batch).
+            eikonal_points = rng.uniform((R, 3), -self.scene_bounding_sphere, self.scene_bounding_sphere)
+            eik_near_points = F.ray_points(cam_loc, ray_dirs, z_samples_eik).reshape(-1, 3)
+            all_points = torch.cat([points_flat, eikonal_points, eik_near_points], 0)
+            y, sdf_all, grad_all = self.implicit_network.outputs_fused(all_points, clamp=n_main)
+            sdf, gradients, grad_theta = sdf_all[:n_main], grad_all[:n_main], grad_all[n_main:]
+        else:
+            y, sdf, gradients = self.implicit_network.outputs_fused(points_flat, clamp=True)
         rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, y, _feat_col=1)
         weights, rgb_values, depth_values, normal_map, _ = F.composite(
             z_vals, sdf, rgb_flat, self.density.beta, float(self.density.beta_min), depth_scale,
@@ -235,11 +245,7 @@ class VolSDFNetwork(nn.Module):
             'xyz': points,
         }
         if self.training:
-            # eikonal samples: R uniform points in the bounding box + one near-surface point per ray
-            eikonal_points = rng.uniform((R, 3), -self.scene_bounding_sphere, self.scene_bounding_sphere)
-            eik_near_points = F.ray_points(cam_loc, ray_dirs, z_samples_eik).reshape(-1, 3)
-            eikonal_points = torch.cat([eikonal_points, eik_near_points], 0)
-            output['grad_theta'] = self.implicit_network.gradient(eikonal_points)
+            output['grad_theta'] = grad_theta
         else:
             output['normal_map'] = normal_map
         return output
