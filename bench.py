@@ -323,6 +323,10 @@ def run_ours(args):
     model.rng_source = None
     pk = peaks()
     roofline, kernels = None, {}
+    traffic_tab = {}
+    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tp):
+        traffic_tab = json.load(open(tp))     # per-launch dram bytes of each kernel from the committed ncu --set full capture
     if prof:
         tot_ms = sum(v['ms'] for v in prof.values())
         for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
@@ -332,13 +336,30 @@ def run_ours(args):
         if v['flops'] > 0:
             ach = v['flops'] / (v['ms'] * 1e-3) / 1e12
             roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops_sustained'],
-                        'unit': 'TFLOP/s', 'frac': ach / pk['tflops_sustained'], 'traffic': None,
+                        'unit': 'TFLOP/s', 'frac': ach / pk['tflops_sustained'], 'traffic': traffic_tab.get(name),
                         'avg_launch_ms': v['ms'] / v['launches'], 'peak_source': pk['source'] + ' bf16 sustained'}
         else:
             ach = v['bytes'] / (v['ms'] * 1e-3) / 1e9
             roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                        'frac': ach / pk['hbm_gbs'], 'traffic': None, 'avg_launch_ms': v['ms'] / v['launches'],
+                        'frac': ach / pk['hbm_gbs'], 'traffic': traffic_tab.get(name), 'avg_launch_ms': v['ms'] / v['launches'],
                         'peak_source': pk['source']}
+
+    # ---- the fp32 parity engine on the same step, for reference (not the headline) ----
+    parity = None
+    if engine != L.ENGINE_FP32 and world == 1:
+        model.set_engine(L.ENGINE_FP32)
+        for i in range(2):
+            step_device(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(3):
+            step_device(W + i % max(K, n_prof))
+        e1.record()
+        torch.cuda.synchronize()
+        parity = {'engine': 'fp32 SIMT (parity mode)', 'ms_per_step': e0.elapsed_time(e1) / 3,
+                  'rays_per_s': Rg / (e0.elapsed_time(e1) / 3 * 1e-3)}
+        model.set_engine(engine)
+    model.rng_source = None
 
     if rank != 0:
         if world > 1:
@@ -356,13 +377,13 @@ def run_ours(args):
         'config': {'workload': 'DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
                                'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam', 'rays_per_gpu': R,
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
-                   'l2': 'per-step working set (~3 GB of saved activations) exceeds the 126 MB L2; no explicit flush',
+                   'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
                    'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)'},
         'e2e': {'value': Rg / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         'algorithmic_tflops': step_tflops, 'algorithmic_frac_of_tensor_peak': step_tflops * 1.0 / world / pk['tflops_sustained'],
-        'kernels': kernels,
+        'kernels': kernels, 'parity_engine': parity,
     }
     print(json.dumps(line))
     if world > 1:
