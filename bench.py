@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc'])
     ap.add_argument('--cpu-rays', type=int, default=128, help='rays per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='issue every step from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -213,7 +214,7 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, capturable=not args.eager)
     reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
     inp_host = S.make_input('dtu', Rg, pixels='perm' if Rg > 4096 else 'random')
     gt_host = S.gt_rgb(Rg)
@@ -253,12 +254,39 @@ def run_ours(args):
     model.rng_source = None
     torch.cuda.synchronize()
 
-    def step_device(i):
+    def step_eager(i):
         model.rng_source = RecordedRng(dev, tapes[i])
         out = model(inp_dev, fast=1)
         finish(loss_of(out, gt_dev))
 
+    # launches of this library per step (counted on one eager step; a graph replay re-issues exactly these)
+    l0 = L.launch_count()
+    step_eager(0)
+    torch.cuda.synchronize()
+    launches_per_step = L.launch_count() - l0
+
+    graphed, step_mode = None, 'eager'
+    if not args.eager:
+        try:
+            from svolsdf_b200.train import GraphedTrainStep
+            graphed = GraphedTrainStep(model, opt, loss_of, inp_dev, gt_dev, grad_clip=1.0, reducer=reducer, world=world,
+                                       make_rng=make_rng)
+            step_mode = 'cuda_graph'
+        except Exception as e:   # keep the run alive, say so in the JSON line
+            graphed, step_mode = None, 'eager (graph capture failed: %s)' % (str(e).splitlines()[0][:120],)
+            model.rng_source = None
+
+    def step_device(i):
+        if graphed is not None:
+            graphed(draws=tapes[i])     # inputs + this step's random draws already resident in HBM
+        else:
+            step_eager(i)
+
     def step_e2e():
+        if graphed is not None:
+            draws = graphed.draw()      # host RNG in the reference's order -> pinned -> device
+            loss = graphed(inp_pin, gt_pin, draws)
+            return float(loss.item()), graphed.h2d_bytes_rng
         model.rng_source = make_rng()
         inp = {k: v.to(dev, non_blocking=True) for k, v in inp_pin.items()}
         gt = gt_pin.to(dev, non_blocking=True)
@@ -285,14 +313,13 @@ def run_ours(args):
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    l0 = L.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
         step_device(W + i)
     e1.record()
     barrier()
-    launches = L.launch_count() - l0
+    launches = launches_per_step * K
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop()
     ms_step = ms_total / K
@@ -316,7 +343,7 @@ def run_ours(args):
     # ---- per-kernel profile pass (CUDA events around every launch of the library; not part of the timing) ----
     L.prof_enable(True)
     for i in range(n_prof):
-        step_device(W + i)
+        step_eager(W + i)
     torch.cuda.synchronize()
     prof = L.prof_collect()
     L.prof_enable(False)
@@ -349,11 +376,11 @@ def run_ours(args):
     if engine != L.ENGINE_FP32 and world == 1:
         model.set_engine(L.ENGINE_FP32)
         for i in range(2):
-            step_device(i)
+            step_eager(i)
         torch.cuda.synchronize()
         e0.record()
         for i in range(3):
-            step_device(W + i % max(K, n_prof))
+            step_eager(W + i % max(K, n_prof))
         e1.record()
         torch.cuda.synchronize()
         parity = {'engine': 'fp32 SIMT (parity mode)', 'ms_per_step': e0.elapsed_time(e1) / 3,
@@ -378,7 +405,8 @@ def run_ours(args):
                                'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam', 'rays_per_gpu': R,
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
-                   'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)'},
+                   'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)',
+                   'step_mode': step_mode},
         'e2e': {'value': Rg / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,

@@ -34,7 +34,8 @@ constexpr int kTile = 128;            // points per tile = MMA M
 constexpr int kBlk = 16384;           // one 64-column block of a 128-row tile image
 constexpr int kMaxKB = 5;             // widest A operand: 320 columns
 constexpr int kWSlots = 2, kWSlot = 32768;
-constexpr int kXSlots = 3, kXSlot = 16384;
+constexpr int kXSlots = 3, kXSlot = 16384;   // aux ring; chains with two aux tiles per block use a 4th slot (kXSlotsMax)
+constexpr int kXSlotsMax = 4;                // ... that overlays the stash region (unused by those chains)
 constexpr int kThreads = 640;         // 4 control warps + 16 epilogue warps
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -254,8 +255,8 @@ __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 }
 
 struct Bars {   // must fit the 512 bytes reserved at kOffBar
-  uint64_t w_full[kWSlots], w_empty[kWSlots], x_full[kXSlots], x_empty[kXSlots], a_ready[kMaxKB * 4], s_free[kMaxKB], acc_full,
-      a_load;
+  uint64_t w_full[kWSlots], w_empty[kWSlots], x_full[kXSlotsMax], x_empty[kXSlotsMax], a_ready[kMaxKB * 4], s_free[kMaxKB],
+      acc_full, a_load, z_ready[kXSlotsMax];   // z_ready[slot]: zeta written into aux slot `slot` by all epilogue warps
   uint32_t tmem;
 };
 
@@ -275,10 +276,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
   Bars* bars = reinterpret_cast<Bars*>(smem + kOffBar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // two aux tiles per block (tangent / backward sweeps): 4 ring slots = two blocks of look-ahead over HBM latency
+  constexpr int XS = (EPI & (epi_bit(EP_TANGENT) | epi_bit(EP_BACKWARD))) ? kXSlotsMax : kXSlots;
+  static_assert(XS == kXSlots || (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD))) == 0, "4th aux slot overlays the stash");
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWSlots; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < kXSlots; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kEpiWarps); }
+    for (int i = 0; i < kXSlotsMax; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kEpiWarps); }
+    for (int i = 0; i < kXSlotsMax; ++i) mbar_init(&bars->z_ready[i], kEpiWarps);
     for (int i = 0; i < kMaxKB * 4; ++i) mbar_init(&bars->a_ready[i], kEpiWarps / 4);   // one per 16-column quarter
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->s_free[i], 1);
     mbar_init(&bars->acc_full, 1);
@@ -359,8 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             for (int a = 0; a < 2; ++a) {
               const int id = a ? st.aux2 : st.aux1;
               if (id < 0) continue;
-              const int slot = seq % kXSlots;
-              const uint32_t use = seq / kXSlots;
+              const int slot = seq % XS;
+              const uint32_t use = seq / XS;
               ++seq;
               mbar_wait(&bars->x_empty[slot], (use & 1) ^ 1);
               mbar_arrive_expect_tx(&bars->x_full[slot], kBlk);
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     // ===== store warp: saves every generation of the A tile (bulk store straight from smem) and hands the blocks
     //       back to the epilogue (s_free) once the async proxy has read them =====
     if (lane == 0) {
-      uint32_t a_par = 0;
+      uint32_t a_par = 0, z_par = 0, xs_seq = 0;
       auto consume = [&](int kb) {
         for (int bi = kb * 4; bi < kb * 4 + 4; ++bi) {
           mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
@@ -394,6 +399,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           const TcStep& st = ch.st[s];
           if (st.next_kb > 0) {
             for (int c = 0; c < st.next_kb; ++c) {
+              if ((EPI & epi_bit(EP_TANGENT)) && st.epi == EP_TANGENT && c < ((st.n_pad + 63) >> 6)) {
+                // zeta block c was written over the U block in its aux slot by all epilogue warps
+                const int slot2 = (xs_seq + 1) % XS;
+                xs_seq += 2;
+                mbar_wait(&bars->z_ready[slot2], (z_par >> slot2) & 1);
+                z_par ^= 1u << slot2;
+                bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk, sX + slot2 * kXSlot, kBlk);
+                bulk_commit();
+                bulk_wait_read<0>();
+                mbar_arrive_n(&bars->x_empty[slot2], kEpiWarps);
+              }
               consume(c);
               if (st.save >= 0) {
                 bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes + (size_t)c * kBlk, sA + c * kBlk, kBlk);
@@ -601,13 +617,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; ++i) a2[i] = 0.f;
             if (c < nchunk_acc && st.aux1 >= 0) {
-              slot1 = xseq % kXSlots;
-              mbar_wait(&bars->x_full[slot1], (xseq / kXSlots) & 1);
+              slot1 = xseq % XS;
+              mbar_wait(&bars->x_full[slot1], (xseq / XS) & 1);
               ++xseq;
               ld_row16(sX + slot1 * kXSlot, m, cq, a1);
               if (st.aux2 >= 0) {
-                slot2 = xseq % kXSlots;
-                mbar_wait(&bars->x_full[slot2], (xseq / kXSlots) & 1);
+                slot2 = xseq % XS;
+                mbar_wait(&bars->x_full[slot2], (xseq / XS) & 1);
                 ++xseq;
                 ld_row16(sX + slot2 * kXSlot, m, cq, a2);
               }
@@ -743,22 +759,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           // release the aux slots
           if (slot1 >= 0) {
             if ((EPI & epi_bit(EP_TANGENT)) && st.epi == EP_TANGENT) {
-              // all warps have rewritten slot2 -> one bulk store, then both slots go back to the producer
+              // zeta sits in slot2: the store warp ships it (after all 16 warps arrived) and frees the slot
               fence_proxy_async();
-              named_bar_sync(2, kEpiThreads);
-              if (leader) {
-                bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk,
-                         sX + slot2 * kXSlot, kBlk);
-                bulk_commit();
-                bulk_wait_read<0>();
+              __syncwarp();
+              if (lane == 0) {
+                mbar_arrive(&bars->z_ready[slot2]);   // per slot: a single barrier would mix arrivals of different blocks
+                mbar_arrive(&bars->x_empty[slot1]);
               }
-              named_bar_sync(2, kEpiThreads);
             } else {
               __syncwarp();
-            }
-            if (lane == 0) {
-              mbar_arrive(&bars->x_empty[slot1]);
-              if (slot2 >= 0) mbar_arrive(&bars->x_empty[slot2]);
+              if (lane == 0) {
+                mbar_arrive(&bars->x_empty[slot1]);
+                if (slot2 >= 0) mbar_arrive(&bars->x_empty[slot2]);
+              }
             }
           }
         }

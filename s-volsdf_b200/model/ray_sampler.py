@@ -70,7 +70,7 @@ class TapeRng(object):
     """Wraps a RefRng-like source and records the device tensors it hands out (to build RecordedRng tapes)."""
 
     def __init__(self, inner):
-        self.inner, self.tape = inner, []
+        self.inner, self.tape, self.calls = inner, [], []
 
     @property
     def h2d_bytes(self):
@@ -81,15 +81,19 @@ class TapeRng(object):
         return t
 
     def rand(self, *shape):
+        self.calls.append(('rand', shape))
         return self._rec(self.inner.rand(*shape))
 
     def randperm(self, n):
+        self.calls.append(('randperm', (n,)))
         return self._rec(self.inner.randperm(n))
 
     def randint(self, high, shape):
+        self.calls.append(('randint', (high, shape)))
         return self._rec(self.inner.randint(high, shape))
 
     def uniform(self, shape, lo, hi):
+        self.calls.append(('uniform', (shape, lo, hi)))
         return self._rec(self.inner.uniform(shape, lo, hi))
 
 
