@@ -38,6 +38,10 @@ def parse():
     ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc'])
     ap.add_argument('--cpu-rays', type=int, default=128, help='rays per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='train', choices=['train', 'frame'],
+                    help="train: BASELINE configs[1] (default, the headline); frame: configs[2], 1600x1200 full-image render")
+    ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
+    ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
     ap.add_argument('--eager', action='store_true', help='issue every step from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -418,9 +422,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+F_SDF, F_RENDER = 1049088.0, 533504.0   # FLOP per point-forward, SURVEY.md Appendix B
+
+
+def run_frame(args):
+    """BASELINE configs[2]: 1600x1200 DTU full-image render (rgb + depth + normal), ray-sharded over the ranks."""
+    import torch.distributed as dist
+    import svolsdf_b200._lib as L
+    import svolsdf_b200.conf as C
+    import svolsdf_b200.scene as S
+    from svolsdf_b200.model.network import VolSDFNetwork
+    from svolsdf_b200.render import render_image
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    engine = L.ENGINE_FP32 if args.engine == 'fp32' else L.ENGINE_TC
+    torch.manual_seed(0)
+    model = VolSDFNetwork(C.dtu_model_conf())
+    if args.beta is not None:
+        S.perturb_(model, w_std=0.0, b_std=0.0, beta=args.beta)
+    model = model.to(dev).eval().set_engine(engine)
+    Wd, Ht = 1600, 1200
+    inp = S.make_input('dtu', Wd * Ht, width=Wd, height=Ht, pixels='grid')
+    K_, pose, uv = inp['intrinsics'].to(dev), inp['pose'].to(dev), inp['uv'].to(dev)
+    R = uv.shape[1]
+    K, W = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.manual_seed(7)
+    for _ in range(W):
+        out = render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop()
+    iters = out['sampler_iters']
+    if rank == 0:
+        pk = peaks()
+        mean_it = sum(iters) / max(len(iters), 1)
+        flop = R * (mean_it * 128 * F_SDF + 98 * (2 * F_SDF + F_RENDER))
+        tf = flop / (ms * 1e-3) / 1e12
+        print(json.dumps({
+            'metric': 'ms/frame 1600x1200 render', 'value': ms, 'unit': 'ms/frame', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f16' if engine == L.ENGINE_TC else 'f32', 'data': 'synthetic',
+            'config': {'workload': 'DTU 1600x1200 full-image render (BASELINE configs[2]): rgb + depth + normal, %d rays, '
+                                   'chunks of %d rays per model call' % (R, args.chunk), 'beta': args.beta,
+                       'sampler_iterations_mean': mean_it, 'parallelism': 'ray-sharded dp%d + all-gather of 28 B/ray' % world},
+            'rays_per_s': R / (ms * 1e-3), 'clocks': clk,
+            'roofline': {'bound': 'tensor', 'achieved': tf / world, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                         'frac': tf / world / pk['tflops_sustained'], 'traffic': None, 'kernel': 'whole frame (algorithmic FLOP)'},
+            'rgb_mean': float(out['rgb_values'].mean()), 'depth_mean': float(out['depth_values'].mean())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
+    elif a.workload == 'frame':
+        run_frame(a)
     else:
         run_ours(a)
