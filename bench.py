@@ -218,7 +218,9 @@ def run_ours(args):
 
     torch.manual_seed(0)
     model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4, capturable=not args.eager)
+    # clip_grad_norm_(1.0) + NaN guard + Adam of vsdf.py:214-219 as one fused step (svolsdf_b200.optim.FusedAdam)
+    from svolsdf_b200.optim import FusedAdam
+    opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
     reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
     inp_host = S.make_input('dtu', Rg, pixels='perm' if Rg > 4096 else 'random')
     gt_host = S.gt_rgb(Rg)
@@ -239,8 +241,7 @@ def run_ours(args):
         loss.backward()
         if reducer is not None:
             reducer.allreduce_(world)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
+        opt.step()      # gradient clipping to norm 1.0 happens inside the fused step
 
     def make_rng():
         return sdist.ShardedRng(dev, Rg, lo, hi) if world > 1 else RefRng(dev)
@@ -273,7 +274,7 @@ def run_ours(args):
     if not args.eager:
         try:
             from svolsdf_b200.train import GraphedTrainStep
-            graphed = GraphedTrainStep(model, opt, loss_of, inp_dev, gt_dev, grad_clip=1.0, reducer=reducer, world=world,
+            graphed = GraphedTrainStep(model, opt, loss_of, inp_dev, gt_dev, grad_clip=0.0, reducer=reducer, world=world,
                                        make_rng=make_rng)
             step_mode = 'cuda_graph'
         except Exception as e:   # keep the run alive, say so in the JSON line

@@ -25,6 +25,7 @@ extern "C" {
 #endif
 
 #define SVS_MAX_LAYERS 12
+#define SVS_OPT_MAX_TENSORS 96
 #define SVS_ABI_VERSION 3
 
 typedef enum {
@@ -230,6 +231,17 @@ int svs_density_forward(const float* sdf, int64_t R, int32_t S, const float* bet
 int svs_density_backward(const float* sdf, int64_t R, int32_t S, const float* beta_param, float beta_min,
                          const float* beta_rows, int32_t abs_density, const float* d_out, float* d_sdf,
                          float* d_beta_param, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Optimiser step of the reference's loop (volsdf/vsdf.py:214-219,454-464): clip_grad_norm_(max_norm) + the NaN/Inf
+ * guard (non-finite gradients are zeroed, Adam still steps) + torch.optim.Adam (no amsgrad / weight decay) for all
+ * parameter tensors in two launches.  Arrays of n_tensors HOST pointers to device tensors; *step_count = number of
+ * this step (device float, incremented by the caller); scratch = 2 device floats (sum g^2, non-finite flag; the
+ * pre-clip norm is sqrt(scratch[0]) afterwards).  max_norm <= 0 disables clipping.
+ * ------------------------------------------------------------------------------------------------- */
+int svs_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                  float max_norm, int32_t skip_nonfinite, const float* step_count, float* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I../../include -I. ${SVS_NVCC_EXTRA:-}"
 mkdir -p build
 pids=()
-for f in capi mlp; do
+for f in capi mlp optim; do
   $NVCC $ARCH $COMMON -Xptxas -v -c $f.cu -o build/$f.o > build/$f.log 2>&1 & pids+=($!)
 done
 for f in sampler composite rays; do

@@ -224,9 +224,21 @@ __global__ void amax_kernel(const AmaxArgs a, uint32_t* __restrict__ out) {
   float m = 0.f;
   for (int k = 0; k < 3; ++k) {
     if (!a.p[k]) continue;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n[k]; i += (long long)gridDim.x * blockDim.x) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    long long head = 0;
+    if ((reinterpret_cast<uintptr_t>(a.p[k]) & 15) == 0) {   // 128-bit loads over the aligned bulk
+      const float4* p4 = reinterpret_cast<const float4*>(a.p[k]);
+      const long long n4 = a.n[k] >> 2;
+      for (long long i = tid; i < n4; i += nthr) {
+        const float4 q = __ldg(p4 + i);
+        float v = fmaxf(fmaxf(fabsf(q.x), fabsf(q.y)), fmaxf(fabsf(q.z), fabsf(q.w))) * a.mult[k];
+        if (v < 3.0e38f) m = fmaxf(m, v);   // ignores inf / nan
+      }
+      head = n4 << 2;
+    }
+    for (long long i = head + tid; i < a.n[k]; i += nthr) {
       float v = fabsf(a.p[k][i]) * a.mult[k];
-      if (v < 3.0e38f) m = fmaxf(m, v);   // ignores inf / nan
+      if (v < 3.0e38f) m = fmaxf(m, v);
     }
   }
   m = warp_max(m);
@@ -236,7 +248,7 @@ static int launch_amax(const float* p0, int64_t n0, float m0, const float* p1, i
                        int64_t n2, float m2, uint32_t* out, cudaStream_t st) {
   SVS_CUDA_OK(cudaMemsetAsync(out, 0, 4, st));
   AmaxArgs a = {{p0, p1, p2}, {n0, n1, n2}, {m0, m1, m2}};
-  amax_kernel<<<4 * kNumSMs, 256, 0, st>>>(a, out);
+  amax_kernel<<<8 * kNumSMs, 256, 0, st>>>(a, out);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

@@ -1,0 +1,58 @@
+"""`FusedAdam`: torch.optim.Adam whose step() is ONE call into the library — gradient clipping by global norm, the
+reference's NaN/Inf guard and the Adam update for all parameter tensors in two launches
+(volsdf/vsdf.py:214-219,454-464 issue clip_grad_norm_, one isnan/isinf host sync per parameter, and Adam.step).
+
+State layout (`exp_avg`, `exp_avg_sq`, `step` as a device tensor) and `state_dict()` are those of
+`torch.optim.Adam(capturable=True)`, so the reference's optimizer checkpoints load unchanged.  CUDA-graph safe.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+class FusedAdam(torch.optim.Adam):
+    def __init__(self, params, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.0, skip_nonfinite=True):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, capturable=True, foreach=False)
+        self.max_grad_norm = float(max_grad_norm)
+        self.skip_nonfinite = bool(skip_nonfinite)
+        self._scratch = None
+        self.last_grad_norm_sq = None   # device tensor: sum of squared gradients of the last step (before clipping)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps = [p for p in group['params'] if p.grad is not None]
+            if not ps:
+                continue
+            if len(ps) > 96:
+                raise L.SvsError('FusedAdam: more than 96 tensors in a parameter group')
+            dev = ps[0].device
+            for p in ps:
+                st = self.state[p]
+                if len(st) == 0:
+                    st['step'] = torch.zeros((), dtype=torch.float32, device=dev)
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if not (p.is_contiguous() and p.grad.is_contiguous()):
+                    raise L.SvsError('FusedAdam needs contiguous parameters and gradients')
+            if self._scratch is None or self._scratch.device != dev:
+                self._scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+            steps = [self.state[p]['step'] for p in ps]
+            torch._foreach_add_(steps, 1.0)      # every tensor of a group carries the same count, as in torch
+            n = len(ps)
+            arr = C.c_void_p * n
+            i64 = C.c_int64 * n
+            L.call('svs_adam_step', n, arr(*[p.data_ptr() for p in ps]), arr(*[p.grad.data_ptr() for p in ps]),
+                   arr(*[self.state[p]['exp_avg'].data_ptr() for p in ps]),
+                   arr(*[self.state[p]['exp_avg_sq'].data_ptr() for p in ps]), i64(*[p.numel() for p in ps]),
+                   float(group['lr']), float(group['betas'][0]), float(group['betas'][1]), float(group['eps']),
+                   self.max_grad_norm, 1 if self.skip_nonfinite else 0, steps[0].data_ptr(), self._scratch.data_ptr(),
+                   L.stream())
+            self.last_grad_norm_sq = self._scratch[0]
+        return loss

@@ -1,0 +1,60 @@
+"""FusedAdam (clip + NaN guard + Adam in two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.Adam."""
+import pytest
+import torch
+
+from svolsdf_b200.optim import FusedAdam
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _params(seed):
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(256, 39), (256,), (256, 1), (217, 256), (257, 256), (3, 256), (), (5000,), (1,)]
+    return [torch.nn.Parameter(torch.randn(s, generator=g).to(DEV)) for s in shapes]
+
+
+@pytest.mark.parametrize('max_norm', [0.0, 1.0])
+def test_matches_torch_adam_and_clip(max_norm):
+    a, b = _params(0), _params(0)
+    ref = torch.optim.Adam(a, lr=5e-4)
+    fus = FusedAdam(b, lr=5e-4, max_grad_norm=max_norm)
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        scale = 10.0 if it % 2 == 0 else 1e-3     # above and below the clipping threshold
+        for pa, pb in zip(a, b):
+            gr = (torch.randn(pa.shape, generator=g) * scale).to(DEV)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        if max_norm > 0:
+            n_ref = torch.nn.utils.clip_grad_norm_(a, max_norm)
+        ref.step()
+        fus.step()
+        if max_norm > 0:
+            assert abs(float(fus.last_grad_norm_sq.sqrt()) - float(n_ref)) < 1e-4 * float(n_ref)
+        for pa, pb in zip(a, b):
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7), it
+    sa, sb = ref.state_dict(), fus.state_dict()
+    assert set(sa['state'][0].keys()) == set(sb['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
+    assert float(sb['state'][0]['step']) == 4.0
+
+
+def test_nonfinite_gradients_are_zeroed_but_adam_still_steps():
+    """volsdf/vsdf.py:454-464: a NaN/Inf gradient zeroes all gradients of the step; Adam.step() still runs"""
+    a, b = _params(2), _params(2)
+    ref = torch.optim.Adam(a, lr=5e-4)
+    fus = FusedAdam(b, lr=5e-4, max_grad_norm=1.0)
+    for it in range(2):
+        for i, (pa, pb) in enumerate(zip(a, b)):
+            gr = torch.ones_like(pa) * 0.01
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        if it == 1:
+            b[3].grad[5, 7] = float('nan')
+            for pa in a:
+                pa.grad.zero_()
+        else:
+            torch.nn.utils.clip_grad_norm_(a, 1.0)
+        ref.step()
+        fus.step()
+        for pa, pb in zip(a, b):
+            assert torch.isfinite(pb).all()
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7)

@@ -47,3 +47,21 @@ if os.environ.get('PROFILE'):
     pr.disable()
     torch.cuda.synchronize()
     pstats.Stats(pr).sort_stats('cumulative').print_stats(35)
+if os.environ.get('KPROF'):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+    rows = []
+    for e in prof.key_averages():
+        ct = getattr(e, 'device_time_total', None)
+        if ct is None:
+            ct = getattr(e, 'cuda_time_total', 0)
+        if ct > 0 and e.device_type.name == 'CUDA':
+            rows.append((ct / 5.0, e.count / 5.0, e.key[:90]))
+    rows.sort(reverse=True)
+    tot = sum(r[0] for r in rows)
+    print('total device us/step %.1f' % tot)
+    for r in rows[:45]:
+        print('%9.1f us  x%5.1f  %s' % r)
