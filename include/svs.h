@@ -201,6 +201,7 @@ int svs_sampler_finalize(const svs_sampler_cfg* c, int64_t R, int32_t n, int32_t
  * bg variants network_bg.py:147-180).  One warp per ray.
  *   flags: SVS_COMP_ABS_DENSITY  sigma=|s| (AbsDensity) instead of Laplace
  *          SVS_COMP_REVERSED     dists = z[i]-z[i+1] (flipped inverse-sphere samples, network_bg.py:170)
+ *          SVS_COMP_FAST         opt-in throughput arithmetic (MUFU exp, fp32 scans); weights differ by ~1e-6
  *          SVS_COMP_ZMAX_TAIL    last dist = z_max - z[S-1] and bg_transmittance output (network_bg.py:152-162)
  *   beta_param: device scalar (density.beta); beta = |beta_param| + beta_min.
  *   outputs: weights (R,S), rgb_values (R,3), depth_values (R) = depth_scale*sum(w z)/(sum(w)+1e-8),
@@ -212,6 +213,7 @@ int svs_sampler_finalize(const svs_sampler_cfg* c, int64_t R, int32_t n, int32_t
 #define SVS_COMP_ABS_DENSITY 1
 #define SVS_COMP_REVERSED 2
 #define SVS_COMP_ZMAX_TAIL 4
+#define SVS_COMP_FAST 8 /* MUFU exp + fp32 scans instead of the oracle's canonical arithmetic (libm exp, fp64 prefix sums) */
 int svs_composite_forward(const float* z, const float* sdf, const float* rgb, const float* normals,
                           const float* beta_param, float beta_min, const float* depth_scale,
                           const float* z_max, int64_t R, int32_t S, int32_t flags, float* weights,

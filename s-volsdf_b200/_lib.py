@@ -14,7 +14,7 @@ SVS_MAX_LAYERS = 12
 ENGINE_FP32, ENGINE_TC = 0, 1
 NET_SDF, NET_RENDER = 0, 1
 RENDER_IDR, RENDER_NERF = 0, 1
-COMP_ABS_DENSITY, COMP_REVERSED, COMP_ZMAX_TAIL = 1, 2, 4
+COMP_ABS_DENSITY, COMP_REVERSED, COMP_ZMAX_TAIL, COMP_FAST = 1, 2, 4, 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('SVS_LIB_PATH') or os.path.join(_HERE, 'libsvolsdf_b200.so')

@@ -5,6 +5,8 @@
 //
 // Reference: density.py:21-35, network.py:281-295 (volume_rendering), :239-248 (rgb/depth),
 // :270-276 (normal map), network_bg.py:147-180 (fg tail + bg pass).  Math of the backward: SURVEY.md App. G.
+#include <type_traits>
+
 #include "svs_common.cuh"
 
 namespace svs {
@@ -23,12 +25,21 @@ __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min
   return fabsf(__ldg(beta_param)) + beta_min;  // density.py:28-30
 }
 
+// FAST (SVS_COMP_FAST, opt-in; the models do not set it): MUFU exp and fp32 scans instead of the canonical arithmetic
+// (libm expf, fp64 prefix sums) that reproduces the oracle; |weights| differ by ~1e-6.  Measured gain at 262144 rays:
+// 5-8 % — the kernels are bound by per-ray instruction count, not by the transcendentals.
+template <bool FAST>
+__device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
+
 // sigma and the autograd-form derivative d sigma / d s
+template <bool FAST = false>
 __device__ __forceinline__ float density_fwd(float s, float beta, bool abs_density, float* em_out) {
   if (abs_density) {
     *em_out = 0.f;
     return fabsf(s);
   }
+  // expm1f stays the libm one even in FAST mode: with the reference's last interval of 1e10 (network.py:286) the
+  // rounding of em and em + 1 is amplified by 1e10 in d beta, and parity means reproducing exactly that rounding
   float em = expm1f(-fabsf(s) / beta);
   *em_out = em;
   float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
@@ -37,28 +48,28 @@ __device__ __forceinline__ float density_fwd(float s, float beta, bool abs_densi
 
 // exclusive prefix sum over the warp's 32*C elements held as v[C] per lane (lane-contiguous layout);
 // returns the grand total.  Accumulates in fp64 like torch's CPU cumsum.
-template <int C>
-__device__ __forceinline__ double warp_excl_scan(const float (&v)[C], double (&excl)[C], int lane) {
-  double run = 0.0;
+template <int C, typename T = double>
+__device__ __forceinline__ T warp_excl_scan(const float (&v)[C], T (&excl)[C], int lane) {
+  T run = 0;
 #pragma unroll
   for (int j = 0; j < C; ++j) {
     excl[j] = run;
-    run += (double)v[j];
+    run += (T)v[j];
   }
-  double incl = run;
+  T incl = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    T t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  double base = __shfl_up_sync(0xffffffffu, incl, 1);  // previous lanes' total (not `incl - run`: cancels)
-  if (lane == 0) base = 0.0;
+  T base = __shfl_up_sync(0xffffffffu, incl, 1);  // previous lanes' total (not `incl - run`: cancels)
+  if (lane == 0) base = 0;
 #pragma unroll
   for (int j = 0; j < C; ++j) excl[j] += base;
   return __shfl_sync(0xffffffffu, incl, 31);
 }
 
-template <int C>
+template <int C, bool FAST>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
                      const float* __restrict__ normals, const float* __restrict__ beta_param, float beta_min,
@@ -84,15 +95,16 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     }
     if (lane == 0) sm.z[warp][32 * C] = 0.f;
     __syncwarp();
+    using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C];
-    double excl[C];
+    ScanT excl[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       float zi = sm.z[warp][i];
       zz[j] = zi;
       float em;
-      float sigma = density_fwd(sm.s[warp][i], beta, abs_d, &em);
+      float sigma = density_fwd<FAST>(sm.s[warp][i], beta, abs_d, &em);
       float d;
       if (i < S - 1) {
         float zn = sm.z[warp][i + 1];
@@ -104,16 +116,15 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       }
       E[j] = (i < S) ? d * sigma : 0.f;
     }
-    double total = warp_excl_scan<C>(E, excl, lane);
+    ScanT total = warp_excl_scan<C, ScanT>(E, excl, lane);
     float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_w = 0.f, acc_wz = 0.f;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float T = expf(-(float)excl[j]);
-      float a = 1.0f - expf(-E[j]);
+      float T = exp_t<FAST>(-(float)excl[j]);
+      float a = 1.0f - exp_t<FAST>(-E[j]);
       float w = (i < S) ? a * T : 0.f;
       if (i < S) {
-        weights[ray * S + i] = w;
         sm.w[warp][i] = w;
         acc_w += w;
         acc_wz += w * zz[j];
@@ -124,6 +135,8 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
         }
       }
     }
+    __syncwarp();
+    for (int i = lane; i < S; i += 32) weights[ray * S + i] = sm.w[warp][i];   // coalesced (the lane-contiguous layout is not)
     acc_w = warp_sum(acc_w);
     acc_wz = warp_sum(acc_wz);
     if (rgb) {
@@ -164,13 +177,13 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
         normal_map[ray * 3 + 1] = ng;
         normal_map[ray * 3 + 2] = nb;
       }
-      if (bg_trans) bg_trans[ray] = expf(-(float)total);
+      if (bg_trans) bg_trans[ray] = exp_t<FAST>(-(float)total);
     }
     __syncwarp();
   }
 }
 
-template <int C>
+template <int C, bool FAST>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
                      const float* __restrict__ beta_param, float beta_min,
@@ -202,15 +215,16 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     const float gdep = d_depth_values ? __ldg(d_depth_values + ray) : 0.f;
     const float gbt = (tail && d_bg_trans) ? __ldg(d_bg_trans + ray) : 0.f;
     const float ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
+    using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C], dl[C], sig[C], em[C], ss[C];
-    double excl[C];
+    ScanT excl[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       float zi = sm.z[warp][i];
       zz[j] = zi;
       ss[j] = sm.s[warp][i];
-      sig[j] = density_fwd(ss[j], beta, abs_d, &em[j]);
+      sig[j] = density_fwd<FAST>(ss[j], beta, abs_d, &em[j]);
       float d;
       if (i < S - 1) {
         float zn = sm.z[warp][i + 1];
@@ -223,14 +237,14 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       dl[j] = d;
       E[j] = (i < S) ? d * sig[j] : 0.f;
     }
-    double total = warp_excl_scan<C>(E, excl, lane);
+    ScanT total = warp_excl_scan<C, ScanT>(E, excl, lane);
     float w[C], Te[C];
     float acc_w = 0.f, acc_wz = 0.f;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float T = expf(-(float)excl[j]);
-      float ee = expf(-E[j]);
+      float T = exp_t<FAST>(-(float)excl[j]);
+      float ee = exp_t<FAST>(-E[j]);
       w[j] = (i < S) ? (1.0f - ee) * T : 0.f;
       Te[j] = T * ee;
       acc_w += w[j];
@@ -254,15 +268,15 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       ww[j] = v * w[j];
     }
     // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
-    double excl2[C];
-    double tot2 = warp_excl_scan<C>(ww, excl2, lane);
-    const float bgt = tail ? expf(-(float)total) : 0.f;
+    ScanT excl2[C];
+    ScanT tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);
+    const float bgt = tail ? exp_t<FAST>(-(float)total) : 0.f;
     float dbeta = 0.f;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       if (i < S) {
-        float suffix = (float)(tot2 - excl2[j] - (double)ww[j]);
+        float suffix = (float)(tot2 - excl2[j] - (ScanT)ww[j]);
         float dE = what[j] * Te[j] - suffix - gbt * bgt;
         float dsig = dl[j] * dE;
         float dsdf;
@@ -275,13 +289,14 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
           dsdf = -dsig * nz * e / (2.0f * beta * beta);
           dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
         }
-        d_sdf[ray * S + i] = dsdf;
+        sm.s[warp][i] = dsdf;   // every lane has its sdf values in registers: reuse the row for the coalesced store
         sm.w[warp][i] = w[j];
       }
     }
     dbeta_acc += dbeta;
+    __syncwarp();
+    for (int i = lane; i < S; i += 32) d_sdf[ray * S + i] = sm.s[warp][i];
     if (d_rgb) {
-      __syncwarp();
       float* o = d_rgb + ray * S * 3;
       for (int i = lane; i < S * 3; i += 32) {
         int e = i / 3, ch = i - 3 * e;
@@ -370,9 +385,15 @@ extern "C" int svs_composite_forward(const float* z, const float* sdf, const flo
   if (R == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_fwd", 0.0, (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (normal_map ? 3 : 0)) + 32), st);
-  DISPATCH_C(S, (composite_fwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
-                    z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
-                    rgb_values, depth_values, normal_map, bg_trans)));
+  if (flags & SVS_COMP_FAST) {
+    DISPATCH_C(S, (composite_fwd_kernel<C, true><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                      z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                      rgb_values, depth_values, normal_map, bg_trans)));
+  } else {
+    DISPATCH_C(S, (composite_fwd_kernel<C, false><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                      z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                      rgb_values, depth_values, normal_map, bg_trans)));
+  }
   SVS_LAUNCH_OK();
   return SVS_OK;
 }
@@ -392,9 +413,15 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_bwd", 0.0,
                (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (d_weights ? 1 : 0) + (d_rgb ? 3 : 0)) + 32), st);
-  DISPATCH_C(S, (composite_bwd_kernel<C><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
-                    z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
-                    d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
+  if (flags & SVS_COMP_FAST) {
+    DISPATCH_C(S, (composite_bwd_kernel<C, true><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                      z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
+                      d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
+  } else {
+    DISPATCH_C(S, (composite_bwd_kernel<C, false><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+                      z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
+                      d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
+  }
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

@@ -329,12 +329,12 @@ static int launch_dw(DwParams& prm, int64_t P, cudaStream_t st) {
     cost[j] = (double)jb.n_pairs * (jb.n_mblk * 2 + jb.n_yblk);   // bytes streamed per tile (the kernel is L2/HBM bound)
     total += cost[j];
   }
-  const int budget = 2 * num_sms();
+  const int budget = num_sms();   // one wave: every CTA streams its share of the tiles once and reduces once
   int unit = 0;
   double flops = 0;
   for (int j = 0; j < prm.n_jobs; ++j) {
     DwJob& jb = prm.job[j];
-    int n = (int)(budget * cost[j] / total + 0.5);
+    int n = (int)(budget * cost[j] / total);   // floor: the total never exceeds one wave
     if (n < 1) n = 1;
     if (n > prm.n_tiles) n = prm.n_tiles;
     jb.unit0 = unit;

@@ -213,7 +213,10 @@ def test_graphed_train_step_matches_eager():
     step = GraphedTrainStep(models[1], opts[1], default_loss, inp, gt, grad_clip=1.0)
     losses_g = [float(step(inp, gt, t)) for t in tapes]
     assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-5, (losses_e, losses_g)
+    # Parameters: Adam's first updates are lr * m / sqrt(v) ~ lr * sign(g), so an entry whose (near-zero) gradient
+    # changes sign with the order of the fp32 atomics in dW moves by up to 2 * lr per step; everything else agrees
+    # to rounding.  Identical kernels, identical inputs: bound the maximum by the 3 steps and require the bulk to match.
     for (n, a), (_, b) in zip(models[0].named_parameters(), models[1].named_parameters()):
-        # Adam divides by sqrt(v): the order of the fp32 atomics in dW moves near-zero gradient entries by ~2 % of one
-        # update (lr = 5e-4); identical kernels, identical inputs
-        assert max_abs(a.detach(), b.detach()) < 1e-4, n
+        d = (a.detach() - b.detach()).abs()
+        assert float(d.max()) <= 3 * 2 * 5e-4 + 1e-6, n
+        assert float((d > 2e-5).float().mean()) < 0.10, n

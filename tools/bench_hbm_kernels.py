@@ -47,16 +47,18 @@ res = []
 
 # compositor forward (training layout: no normals): reads z, sdf, rgb; writes weights, rgb_values, depth_values
 w = torch.empty(R, S, device=dev); rv = torch.empty(R, 3, device=dev); dv = torch.empty(R, 1, device=dev)
-ms = timeit(lambda: L.call('svs_composite_forward', z.data_ptr(), sdf.data_ptr(), rgb.data_ptr(), None, beta.data_ptr(), 1e-4,
-                           ds.data_ptr(), None, R, S, 0, w.data_ptr(), rv.data_ptr(), dv.data_ptr(), None, None, L.stream()))
-res.append(('composite_fwd', 2368.0, ms))
+for fl, tag in ((0, 'exact'), (L.COMP_FAST, 'fast')):
+    ms = timeit(lambda: L.call('svs_composite_forward', z.data_ptr(), sdf.data_ptr(), rgb.data_ptr(), None, beta.data_ptr(), 1e-4,
+                               ds.data_ptr(), None, R, S, fl, w.data_ptr(), rv.data_ptr(), dv.data_ptr(), None, None, L.stream()))
+    res.append(('composite_fwd_' + tag, 2368.0, ms))
 # compositor backward: reads dW, d(rgb, depth), forward inputs; writes d_sdf, d_rgb
 dwt = torch.rand(R, S, device=dev); drv = torch.rand(R, 3, device=dev); ddv = torch.rand(R, 1, device=dev)
 d_sdf = torch.empty(R, S, device=dev); d_rgb = torch.empty(R, S, 3, device=dev); d_beta = torch.zeros(1, device=dev)
-ms = timeit(lambda: L.call('svs_composite_backward', z.data_ptr(), sdf.data_ptr(), rgb.data_ptr(), beta.data_ptr(), 1e-4,
-                           ds.data_ptr(), None, R, S, 0, drv.data_ptr(), ddv.data_ptr(), dwt.data_ptr(), None,
-                           d_sdf.data_ptr(), d_rgb.data_ptr(), d_beta.data_ptr(), L.stream()))
-res.append(('composite_bwd', 3936.0, ms))
+for fl, tag in ((0, 'exact'), (L.COMP_FAST, 'fast')):
+    ms = timeit(lambda: L.call('svs_composite_backward', z.data_ptr(), sdf.data_ptr(), rgb.data_ptr(), beta.data_ptr(), 1e-4,
+                               ds.data_ptr(), None, R, S, fl, drv.data_ptr(), ddv.data_ptr(), dwt.data_ptr(), None,
+                               d_sdf.data_ptr(), d_rgb.data_ptr(), d_beta.data_ptr(), L.stream()))
+    res.append(('composite_bwd_' + tag, 3936.0, ms))
 
 # sampler, training iteration: init (t_rand 512 B in, z 512 B out), bound (z, sdf in; beta out), resample (u in, samples out),
 # finalize (z_98 out): 2212 B/ray in total
