@@ -42,6 +42,7 @@ def parse():
                     help="train: BASELINE configs[1] (default, the headline); frame: configs[2], 1600x1200 full-image render")
     ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
     ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
+    ap.add_argument('--no-parity-leg', action='store_true', help='skip the fp32 parity-engine comparison leg (profiling runs)')
     ap.add_argument('--eager', action='store_true', help='issue every step from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -67,7 +68,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -287,10 +288,15 @@ def run_ours(args):
         else:
             step_eager(i)
 
+    pending = {'draws': None}
+
     def step_e2e():
         if graphed is not None:
-            draws = graphed.draw()      # host RNG in the reference's order -> pinned -> device
+            # host RNG in the reference's order -> pinned -> device.  The draws of step i+1 are made on the CPU while
+            # the GPU replays step i (they only depend on the CPU generator), then the loss of step i is read back.
+            draws = pending['draws'] if pending['draws'] is not None else graphed.draw()
             loss = graphed(inp_pin, gt_pin, draws)
+            pending['draws'] = graphed.draw()
             return float(loss.item()), graphed.h2d_bytes_rng
         model.rng_source = make_rng()
         inp = {k: v.to(dev, non_blocking=True) for k, v in inp_pin.items()}
@@ -378,7 +384,7 @@ def run_ours(args):
 
     # ---- the fp32 parity engine on the same step, for reference (not the headline) ----
     parity = None
-    if engine != L.ENGINE_FP32 and world == 1:
+    if engine != L.ENGINE_FP32 and world == 1 and not args.no_parity_leg:
         model.set_engine(L.ENGINE_FP32)
         for i in range(2):
             step_eager(i)
