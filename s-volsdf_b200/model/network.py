@@ -72,6 +72,7 @@ class ImplicitNetwork(nn.Module):
         self.softplus = nn.Softplus(beta=100)   # kept for interface parity; the kernels fuse it
         self.engine = L.ENGINE_FP32
         self._net = None
+        self._net_raw = None
         if len(self.skip_in) > 1:
             raise NotImplementedError('one skip connection is supported (config/vol/*.yaml use skip_in=[4])')
 
@@ -111,6 +112,18 @@ class ImplicitNetwork(nn.Module):
     def get_outputs(self, x):
         y, sdf, g = F.sdf_outputs(self.net(), x, clamp=True, want_grad=True)
         return sdf, y[:, 1:self.n_out], g
+
+    def sdf_only(self, x):
+        """forward(x)[:, :1] without computing the feature columns (no sphere clamp, no autograd): the bulk query of
+        mesh extraction, `sdf = lambda x: model.implicit_network(x)[:, 0]` (eval_vsdf.py:115,132; utils/plots.py:61)."""
+        if self._net_raw is None or self._net_raw.engine != self.engine:
+            desc = L.make_desc(L.NET_SDF, self._in_dims, self._out_dims, d_in=self.d_in, n_freqs=self.multires,
+                               skip_layer=self.skip_in[0] if self.skip_in else -1, weight_norm=self.weight_norm,
+                               sphere_radius=0.0, sphere_scale=1.0)
+            layers = [_layer_params(getattr(self, 'lin' + str(l))) for l in range(self.num_layers - 1)]
+            self._net_raw = F.NetHandle(desc, layers, self.engine)
+        with torch.no_grad():
+            return F.sdf_forward_nograd(self._net_raw, x, False, True)[1]
 
     def get_sdf_vals(self, x):
         net = self.net()

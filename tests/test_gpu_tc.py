@@ -220,3 +220,32 @@ def test_graphed_train_step_matches_eager():
         d = (a.detach() - b.detach()).abs()
         assert float(d.max()) <= 3 * 2 * 5e-4 + 1e-6, n
         assert float((d > 2e-5).float().mean()) < 0.10, n
+
+
+@pytest.mark.parametrize('engine', [L.ENGINE_FP32, L.ENGINE_TC])
+def test_mesh_grid_query_matches_forward(engine):
+    """svolsdf_b200.mesh.sdf_grid == model.implicit_network(x)[:, 0] (the reference's meshing query, plots.py:61)"""
+    from svolsdf_b200.mesh import sdf_grid
+    m = build_model('dtu', perturb=True, device=DEV).eval().set_engine(engine)
+    grid, axes = sdf_grid(m, resolution=24, bound=1.2, chunk=5000)
+    assert grid.shape == (24, 24, 24)
+    pts = torch.stack(torch.meshgrid(*axes, indexing='ij'), -1).reshape(-1, 3)
+    with torch.no_grad():
+        ref = m.implicit_network(pts)[:, 0]
+    assert max_abs(grid.reshape(-1), ref) < (1e-5 if engine == L.ENGINE_FP32 else 1e-6 + 0)   # same kernels, same engine
+    assert float(grid.min()) < 0 < float(grid.max())       # the surface crosses the box
+
+
+def test_full_frame_render_helper_matches_chunked_model_calls():
+    """svolsdf_b200.render.render_rays == looping the model over `split_input` chunks (vsdf.py:246-262)"""
+    from svolsdf_b200.render import render_rays
+    m = build_model('dtu', perturb=True, beta=0.05, device=DEV).eval().set_engine(L.ENGINE_TC)
+    inp = {k: v.to(DEV) for k, v in S.make_input('dtu', 300).items()}
+    torch.manual_seed(3)
+    got = render_rays(m, inp['intrinsics'], inp['pose'], inp['uv'], chunk=128)
+    torch.manual_seed(3)
+    parts = [m({'intrinsics': inp['intrinsics'], 'pose': inp['pose'], 'uv': inp['uv'][:, lo:lo + 128].contiguous()})
+             for lo in range(0, 300, 128)]
+    for k in ('rgb_values', 'depth_values', 'normal_map'):
+        assert torch.equal(got[k], torch.cat([p[k] for p in parts], 0)), k
+    assert got['rgb_values'].shape == (300, 3) and len(got['sampler_iters']) == 3
