@@ -31,6 +31,48 @@ __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min
 template <bool FAST>
 __device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
 
+// Coalesced staging of a ray's rows into shared memory.  All global loads are issued before the first shared store
+// (registers in between), so a warp keeps C + C + 3C independent 128-byte requests in flight: with one request at a
+// time per warp the kernels reached only a quarter of the HBM bandwidth (latency-bound, profiles/r1_hbm_kernels.json).
+template <int N>
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, int n, int lane, float* dst) {
+  float r[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int i = lane + 32 * j;
+    r[j] = (i < n) ? __ldg(src + i) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) dst[lane + 32 * j] = r[j];
+}
+template <int C>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ zr, const float* __restrict__ sr,
+                                           const float* __restrict__ cr, int S, int lane, float* dz, float* dsd, float* dc) {
+  float rz[C], rs[C], rc[3 * C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int i = lane + 32 * j;
+    rz[j] = (i < S) ? __ldg(zr + i) : 0.f;
+    rs[j] = (i < S) ? __ldg(sr + i) : 0.f;
+  }
+  if (cr) {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) {
+      const int i = lane + 32 * j;
+      rc[j] = (i < 3 * S) ? __ldg(cr + i) : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    dz[lane + 32 * j] = rz[j];
+    dsd[lane + 32 * j] = rs[j];
+  }
+  if (cr) {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) dc[lane + 32 * j] = rc[j];
+  }
+}
+
 // sigma and the autograd-form derivative d sigma / d s
 template <bool FAST = false>
 __device__ __forceinline__ float density_fwd(float s, float beta, bool abs_density, float* em_out) {
@@ -83,16 +125,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
              tail = flags & SVS_COMP_ZMAX_TAIL;
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
   for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
-    const float* zr = z + ray * S;
-    const float* sr = sdf + ray * S;
-    for (int i = lane; i < 32 * C; i += 32) {
-      sm.z[warp][i] = (i < S) ? zr[i] : 0.f;
-      sm.s[warp][i] = (i < S) ? sr[i] : 0.f;
-    }
-    if (rgb) {
-      const float* cr = rgb + ray * S * 3;
-      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = cr[i];
-    }
+    stage_rows<C>(z + ray * S, sdf + ray * S, rgb ? rgb + ray * S * 3 : nullptr, S, lane, sm.z[warp], sm.s[warp], sm.c[warp]);
     if (lane == 0) sm.z[warp][32 * C] = 0.f;
     __syncwarp();
     using ScanT = typename std::conditional<FAST, float, double>::type;
@@ -147,8 +180,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     float nr = 0.f, ng = 0.f, nb = 0.f;
     if (normal_map) {  // eval: sum w * g/|g|  (network.py:270-274; no eps, as the reference)
       __syncwarp();
-      const float* gr = normals + ray * S * 3;
-      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = gr[i];
+      stage_row<3 * C>(normals + ray * S * 3, S * 3, lane, sm.c[warp]);
       __syncwarp();
       for (int i = lane; i < S; i += 32) {
         float gx = sm.c[warp][3 * i], gy = sm.c[warp][3 * i + 1], gz = sm.c[warp][3 * i + 2];
@@ -198,16 +230,8 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
   float dbeta_acc = 0.f;
   for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
-    const float* zr = z + ray * S;
-    const float* sr = sdf + ray * S;
-    for (int i = lane; i < 32 * C; i += 32) {
-      sm.z[warp][i] = (i < S) ? zr[i] : 0.f;
-      sm.s[warp][i] = (i < S) ? sr[i] : 0.f;
-    }
-    if (rgb) {
-      const float* cr = rgb + ray * S * 3;
-      for (int i = lane; i < S * 3; i += 32) sm.c[warp][i] = cr[i];
-    }
+    stage_rows<C>(z + ray * S, sdf + ray * S, rgb ? rgb + ray * S * 3 : nullptr, S, lane, sm.z[warp], sm.s[warp], sm.c[warp]);
+    if (d_weights) stage_row<C>(d_weights + ray * S, S, lane, sm.w[warp]);
     __syncwarp();
     const float gr = d_rgb_values ? __ldg(d_rgb_values + ray * 3) : 0.f;
     const float gg = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 1) : 0.f;
@@ -261,12 +285,13 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       float v = 0.f;
       if (i < S) {
         if (rgb) v = sm.c[warp][3 * i] * gr + sm.c[warp][3 * i + 1] * gg + sm.c[warp][3 * i + 2] * gb;
-        if (d_weights) v += d_weights[ray * S + i];
+        if (d_weights) v += sm.w[warp][i];
         v += gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
       }
       what[j] = v;
       ww[j] = v * w[j];
     }
+    __syncwarp();   // sm.w (staged dL/dweights) is rewritten with w below
     // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
     ScanT excl2[C];
     ScanT tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);

@@ -36,9 +36,9 @@ constexpr int kMaxKB = 5;             // widest A operand: 320 columns
 constexpr int kWSlots = 2, kWSlot = 32768;
 constexpr int kXSlots = 3, kXSlot = 16384;   // aux ring; chains with two aux tiles per block use a 4th slot (kXSlotsMax)
 constexpr int kXSlotsMax = 4;                // ... that overlays the stash region (unused by those chains)
-constexpr int kThreads = 640;         // 4 control warps + 16 epilogue warps
-constexpr int kEpiWarps = 16;
-constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kCtrlThreads = 128;     // 4 control warps; then NW epilogue warps (16 or 24, template parameter)
+constexpr int kPieceWarps = 4;        // a 16-column piece of a block is written by 4 warps (one per TMEM lane quarter)
+constexpr int kChunkWarps = 16;       // ... and a 64-column block by 16
 constexpr int kStashLd = 40;          // fp32 per row: skip-branch / PE-gradient stash (<= 39 + pad)
 constexpr int kMaxSteps = 11;
 constexpr int kMaxImgs = 36;
@@ -194,6 +194,19 @@ __device__ __forceinline__ void ld_row16(const uint8_t* blk, int m, int cq, floa
   }
 }
 
+// the same 16 columns as packed fp16 pairs (8 registers); element i = half (i & 1) of h[i >> 1]
+__device__ __forceinline__ void ld_row16h(const uint8_t* blk, int m, int cq, uint32_t (&h)[8]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u = *reinterpret_cast<const uint4*>(blk + chunk_off(m, cq * 2 + i));
+    h[4 * i + 0] = u.x; h[4 * i + 1] = u.y; h[4 * i + 2] = u.z; h[4 * i + 3] = u.w;
+  }
+}
+__device__ __forceinline__ float h_elem(const uint32_t (&h)[8], int i) {
+  const __half2 v = *reinterpret_cast<const __half2*>(&h[i >> 1]);
+  return (i & 1) ? __high2float(v) : __low2float(v);
+}
+
 constexpr float kSpK1 = 144.26950408889634f;     // 100 * log2(e)
 constexpr float kSpK2 = 0.006931471805599453f;   // ln(2) / 100
 constexpr float kSpThr = 28.853900817779268f;    // 20 * log2(e): Softplus threshold (network.py:69, torch default 20)
@@ -265,8 +278,10 @@ __host__ __device__ constexpr uint32_t epi_bit(int e) { return 1u << e; }
 // ---------------------------------------------------------------------------------------------------------------
 // the chain kernel; EPI / PRO select which epilogues / prologue are compiled into an instantiation
 // ---------------------------------------------------------------------------------------------------------------
-template <uint32_t EPI, int PRO>
-__global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_constant__ TcChain ch) {
+template <uint32_t EPI, int PRO, int NW>
+__global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(const __grid_constant__ TcChain ch) {
+  constexpr int kThreads = kCtrlThreads + NW * 32, kEpiThreads = NW * 32, NCG = NW / 4;   // NCG column groups
+  static_assert(NW % 4 == 0 && NCG >= 4, "every block needs 4 distinct column groups");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + kOffA;
   uint8_t* sW = smem + kOffW;
@@ -282,9 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWSlots; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < kXSlotsMax; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kEpiWarps); }
-    for (int i = 0; i < kXSlotsMax; ++i) mbar_init(&bars->z_ready[i], kEpiWarps);
-    for (int i = 0; i < kMaxKB * 4; ++i) mbar_init(&bars->a_ready[i], kEpiWarps / 4);   // one per 16-column quarter
+    for (int i = 0; i < kXSlotsMax; ++i) { mbar_init(&bars->x_full[i], 1); mbar_init(&bars->x_empty[i], kChunkWarps); }
+    for (int i = 0; i < kXSlotsMax; ++i) mbar_init(&bars->z_ready[i], kChunkWarps);
+    for (int i = 0; i < kMaxKB * 4; ++i) mbar_init(&bars->a_ready[i], kPieceWarps);   // one per 16-column piece
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->s_free[i], 1);
     mbar_init(&bars->acc_full, 1);
     mbar_init(&bars->a_load, 1);
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                 bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk, sX + slot2 * kXSlot, kBlk);
                 bulk_commit();
                 bulk_wait_read<0>();
-                mbar_arrive_n(&bars->x_empty[slot2], kEpiWarps);
+                mbar_arrive_n(&bars->x_empty[slot2], kChunkWarps);
               }
               consume(c);
               if (st.save >= 0) {
@@ -427,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
     }
   } else if (warp >= 4) {
     // ===== epilogue warps =====
-    const int ew = warp - 4, q = ew & 3, cq = ew >> 2;
+    // 16-column pieces p = 0, 1, ... of the step's columns; this warp owns the pieces p = cg (mod NCG)
+    const int ew = warp - 4, q = ew & 3, cg = ew >> 2;
     const int m = q * 32 + lane;
     const int et = threadIdx.x - 128;
     const bool leader = (et == 0);
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
       if (PRO == PRO_PE_JVP && ch.d_grad && live)
         for (int d = 0; d < ch.d_in; ++d) dg[d] = gs * cw * ch.d_grad[p * ch.d_in + d];
       if (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD)))
-        for (int i = cq; i < kStashLd; i += 4) stash[m * kStashLd + i] = 0.f;
+        for (int i = cg; i < kStashLd; i += NCG) stash[m * kStashLd + i] = 0.f;
       if (PRO == PRO_LOAD_ULAST) {
         if (leader) {
           // the blocks must have been saved (previous tile) before the async proxy overwrites them
@@ -488,9 +504,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         mbar_wait(&bars->a_load, n_load & 1);
         ++n_load;
       }
-      for (int b = 0; b < ch.pro_kb; ++b) {
+      for (int pc = cg; pc < ch.pro_kb * 4; pc += NCG) {
         float v[16];
-        const int c0 = b * 64 + cq * 16;
+        const int b = pc >> 2, cq = pc & 3;
+        const int c0 = pc * 16;
         if (PRO == PRO_PE) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_col(xv, ch.d_in, ch.n_freqs, c0 + i) : 0.f;
@@ -566,7 +583,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           }
         }
         mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
-        fgen ^= 1u << b;
         st_row16(sA + b * kBlk, m, cq, v);
         if (ch.pro_colsum >= 0) {
           float cs = warp_colsum16(v, lane);
@@ -574,8 +590,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->a_ready[b * 4 + cq]);
+        if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
       }
+      for (int b = 0; b < ch.pro_kb; ++b) fgen ^= 1u << b;
 
       // ---------------- steps ----------------
       for (int s = 0; s < ch.n_steps; ++s) {
@@ -584,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         const bool has_next = s + 1 < ch.n_steps;
         const bool writes_a = st.next_kb > 0;
         const float c_lo = kSpK2 * st.scale, c_hi = st.scale / kSpK1;
+        const float khs = -kSpK1 * st.hscale;   // s(h * hscale) = 1 - 2^(khs * h)
         const uint32_t tm_acc = tm_row + (n_acc & 1) * 256;
         mbar_wait(&bars->acc_full, n_acc & 1);
         ++n_acc;
@@ -591,15 +609,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
-            for (int c = 0; c < ch.st[s + 1].KB; ++c) mbar_arrive(&bars->a_ready[c * 4 + cq]);
+            for (int pc = cg; pc < ch.st[s + 1].KB * 4; pc += NCG) mbar_arrive(&bars->a_ready[pc]);
         }
 
         const int nchunk_acc = (st.n_pad + 63) >> 6;
         const int nchunk = max(nchunk_acc, st.next_kb);
-        uint32_t rr[16];   // accumulator columns of the NEXT chunk (tcgen05.ld issued one chunk ahead)
-        if (cq * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(cq * 16), rr);
-        for (int c = 0; c < nchunk; ++c) {
-          const int col0 = c * 64 + cq * 16;
+        const int naux = (st.aux1 >= 0 ? 1 : 0) + (st.aux2 >= 0 ? 1 : 0);
+        const uint32_t xbase = xseq;   // aux blocks are numbered (chunk, aux) in the order the producer loads them
+        uint32_t rr[16];   // accumulator columns of this warp's NEXT piece (tcgen05.ld issued one piece ahead)
+        if (cg * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(cg * 16), rr);
+        for (int pc = cg; pc < nchunk * 4; pc += NCG) {
+          const int c = pc >> 2, cq = pc & 3;
+          const int col0 = pc * 16;
           float acc[16];
           if (col0 < st.n_pad) {
             tmem_ld_wait();
@@ -609,23 +630,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
           }
-          if (col0 + 64 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + 64), rr);
+          if (col0 + NCG * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + NCG * 16), rr);
           // aux tiles of this chunk
-          float a1[16], a2[16];
+          uint32_t a1[8], a2[8];   // aux values stay packed (fp16 pairs) until they are used: 16 registers less
           int slot1 = -1, slot2 = -1;
           if (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_RELU_BWD) | epi_bit(EP_TANGENT) | epi_bit(EP_BACKWARD))) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a2[i] = 0.f;
+            for (int i = 0; i < 8; ++i) a1[i] = a2[i] = 0u;
             if (c < nchunk_acc && st.aux1 >= 0) {
-              slot1 = xseq % XS;
-              mbar_wait(&bars->x_full[slot1], (xseq / XS) & 1);
-              ++xseq;
-              ld_row16(sX + slot1 * kXSlot, m, cq, a1);
+              const uint32_t x1 = xbase + (uint32_t)(c * naux);
+              slot1 = x1 % XS;
+              mbar_wait(&bars->x_full[slot1], (x1 / XS) & 1);
+              ld_row16h(sX + slot1 * kXSlot, m, cq, a1);
               if (st.aux2 >= 0) {
-                slot2 = xseq % XS;
-                mbar_wait(&bars->x_full[slot2], (xseq / XS) & 1);
-                ++xseq;
-                ld_row16(sX + slot2 * kXSlot, m, cq, a2);
+                slot2 = (x1 + 1) % XS;
+                mbar_wait(&bars->x_full[slot2], ((x1 + 1) / XS) & 1);
+                ld_row16h(sX + slot2 * kXSlot, m, cq, a2);
               }
             }
           }
@@ -666,24 +686,41 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
                 if (col0 + i < st.n_valid) dst[i] = acc[i] + btab_s[(col0 + i) & 255];
             }
           } else if ((EPI & epi_bit(EP_REVERSE)) && st.epi == EP_REVERSE) {
+            if (col0 + 16 <= st.n_split) {   // whole piece inside the sigma' columns: no per-element predicates
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = col0 + i;
-              const float pv = acc[i] * st.scale;
-              float r = 0.f;
-              if (n < st.n_split) r = dsoftplus_h(a1[i] * st.hscale) * pv;
-              else if (n < st.n_valid) stash[m * kStashLd + (n - st.n_split)] = pv;
-              o[i] = r;
+              for (int i = 0; i < 16; ++i) o[i] = (1.0f - ex2_approx(khs * h_elem(a1, i))) * (acc[i] * st.scale);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                const float pv = acc[i] * st.scale;
+                float r = 0.f;
+                if (n < st.n_split) r = (1.0f - ex2_approx(khs * h_elem(a1, i))) * pv;
+                else if (n < st.n_valid) stash[m * kStashLd + (n - st.n_split)] = pv;
+                o[i] = r;
+              }
             }
           } else if ((EPI & epi_bit(EP_PEGRAD)) && st.epi == EP_PEGRAD) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (col0 + i < st.n_valid) stash[m * kStashLd + col0 + i] += acc[i];
           } else if ((EPI & epi_bit(EP_RELU)) && st.epi == EP_RELU) {
+            if (full) {
+              const float4* b4 = reinterpret_cast<const float4*>(btab_s + col0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = col0 + i;
-              o[i] = (n < st.n_valid) ? fmaxf(acc[i] + btab_s[n & 255], 0.f) : 0.f;
+              for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                o[4 * i + 0] = fmaxf(acc[4 * i + 0] + b.x, 0.f);
+                o[4 * i + 1] = fmaxf(acc[4 * i + 1] + b.y, 0.f);
+                o[4 * i + 2] = fmaxf(acc[4 * i + 2] + b.z, 0.f);
+                o[4 * i + 3] = fmaxf(acc[4 * i + 3] + b.w, 0.f);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                o[i] = (n < st.n_valid) ? fmaxf(acc[i] + btab_s[n & 255], 0.f) : 0.f;
+              }
             }
           } else if ((EPI & epi_bit(EP_RGB)) && st.epi == EP_RGB) {
             if (live) {
@@ -694,8 +731,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
               }
             }
           } else if ((EPI & epi_bit(EP_RELU_BWD)) && st.epi == EP_RELU_BWD) {
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = (a1[i] > 0.f && col0 + i < st.n_valid) ? acc[i] : 0.f;
+              for (int i = 0; i < 16; ++i) o[i] = (h_elem(a1, i) > 0.f) ? acc[i] : 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = (h_elem(a1, i) > 0.f && col0 + i < st.n_valid) ? acc[i] : 0.f;
+            }
           } else if ((EPI & epi_bit(EP_DFEAT)) && st.epi == EP_DFEAT) {
             if (live && ch.d_feat) {
               float* dst = ch.d_feat + p * ch.ld_dfeat + col0;
@@ -713,13 +755,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             }
           } else if ((EPI & epi_bit(EP_TANGENT)) && st.epi == EP_TANGENT) {
             float z[16];
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = col0 + i;
-              const float sg = dsoftplus_h(a1[i] * st.hscale);
-              const bool ok = n < st.n_valid;
-              z[i] = ok ? 100.0f * (1.0f - sg) * a2[i] * acc[i] : 0.f;
-              o[i] = ok ? sg * acc[i] * st.scale : 0.f;
+              for (int i = 0; i < 16; ++i) {
+                const float sg = 1.0f - ex2_approx(khs * h_elem(a1, i));
+                z[i] = 100.0f * (1.0f - sg) * h_elem(a2, i) * acc[i];
+                o[i] = sg * acc[i] * st.scale;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int n = col0 + i;
+                const float sg = 1.0f - ex2_approx(khs * h_elem(a1, i));
+                const bool ok = n < st.n_valid;
+                z[i] = ok ? 100.0f * (1.0f - sg) * h_elem(a2, i) * acc[i] : 0.f;
+                o[i] = ok ? sg * acc[i] * st.scale : 0.f;
+              }
             }
             if (!full && (st.flags & TC_QFILL)) {
 #pragma unroll
@@ -735,22 +786,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
             // zeta overwrites the U block in its aux slot and leaves through a bulk store
             if (slot2 >= 0) st_row16(sX + slot2 * kXSlot, m, cq, z);
           } else if ((EPI & epi_bit(EP_BACKWARD)) && st.epi == EP_BACKWARD) {
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float sg = dsoftplus_h(a1[i] * st.hscale);
-              o[i] = (col0 + i < st.n_valid) ? sg * acc[i] * st.scale + a2[i] : 0.f;
+              for (int i = 0; i < 16; ++i) o[i] = (1.0f - ex2_approx(khs * h_elem(a1, i))) * acc[i] * st.scale + h_elem(a2, i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sg = 1.0f - ex2_approx(khs * h_elem(a1, i));
+                o[i] = (col0 + i < st.n_valid) ? sg * acc[i] * st.scale + h_elem(a2, i) : 0.f;
+              }
             }
           }
           if (writes_a && c < st.next_kb) {
             mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
-            fgen ^= 1u << c;
 #ifndef SVS_DBG_NOSTORE
             st_row16(sA + c * kBlk, m, cq, o);
 #endif
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->a_ready[c * 4 + cq]);
+            if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
             if (st.colsum >= 0) {
               float cs = warp_colsum16(o, lane);
               if (lane < 16) atomicAdd(&colsum[st.colsum * kColsumW + col0 + lane], cs);
@@ -778,7 +833,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
         if ((EPI & epi_bit(EP_PEGRAD)) && st.epi == EP_PEGRAD) {
           // stash now holds p_0 + e for all PE columns of the row: g = J_PE^T (p_0 + e), sphere clamp of sdf and g
           named_bar_sync(2, kEpiThreads);
-          if (cq == 0 && live) {
+          if (cg == 0 && live) {   // the warps that own piece 0 (one thread per row)
             float g[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < pe_w; ++c) {
               int dim;
@@ -797,6 +852,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_chain_kernel(const __grid_cons
           }
           named_bar_sync(2, kEpiThreads);   // the stash is re-zeroed by the next tile's prologue
         }
+        // every warp advances the ring / generation counters of ALL blocks of the step, also those it did not touch
+        if (st.aux1 >= 0) xseq = xbase + (uint32_t)(nchunk_acc * naux);
+        if (writes_a)
+          for (int c = 0; c < st.next_kb; ++c) fgen ^= 1u << c;
         tc_fence_before();
       }
     }

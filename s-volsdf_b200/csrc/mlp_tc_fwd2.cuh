@@ -1,0 +1,362 @@
+// SVS_ENGINE_TC, SDF forward chain, "two tiles in flight" kernel (tc_fwd2_kernel).
+//
+// The generic chain kernel (mlp_tc.cuh) walks ONE 128-point tile at a time, so every layer pays the
+// MMA -> epilogue -> MMA dependency latency and the SM idles between the hand-offs.  The forward chain of the SDF
+// net (ImplicitNetwork.forward / get_sdf_vals / the forward half of get_outputs, volsdf/model/network.py:71-88,
+// 105-131) needs no aux tiles, which leaves room for a second activation tile in shared memory.  This kernel
+// keeps TWO tiles resident and ping-pongs them: while the 16 epilogue warps turn tile 0's accumulator into the
+// next layer's A operand, the tensor pipe multiplies tile 1, and vice versa.  All hand-offs are whole-tile:
+//
+//   a_full[T]   (count = epilogue warps)  A_T holds the operand of the next step and acc_T has been drained
+//   acc_full[T] (tcgen05.commit)          acc_T holds the step's result and A_T has been read by the tensor pipe
+//   s_free[T]   (store lane)              the bulk store that saves A_T (training forward) has read the tile
+//
+// TMEM: acc_T = columns [256 T, 256 T + 256).  Shared memory: A[2][4 blocks] 128 KB, weight ring 2 x 32 KB,
+// bias table, PE column table.  Softplus(beta=100) costs ONE MUFU per element here: with t = 100 z log2(e),
+//   softplus(z) = ln2/100 * ( max(t, 0) + log2(1 + 2^-|t|) ),   log2(1 + u) ~ u q(u) on [0, 1] (|err| <= 1.1e-4,
+// i.e. 7e-7 in the activation — a fifth of an fp16 ulp at the smallest activations the term matters for).
+// The chain description (TcChain) is the one the generic kernel takes; launch_chain() routes PRO_PE chains here.
+#pragma once
+#include "mlp_tc.cuh"
+
+namespace svs {
+namespace tc {
+
+constexpr int kF2MaxKB = 4;                                   // K <= 256
+constexpr int kF2OffA = 0;                                    // A[2][4] blocks
+constexpr int kF2OffW = 2 * kF2MaxKB * kBlk;                  // 131072
+constexpr int kF2OffBtab = kF2OffW + kWSlots * kWSlot;        // 196608
+constexpr int kF2OffPe = kF2OffBtab + kMaxSteps * 256 * 4;    // 207872 : 128 PE column entries of 8 bytes
+constexpr int kF2PeCols = 128;
+constexpr int kF2OffBar = kF2OffPe + kF2PeCols * 8;           // 208896
+constexpr int kF2SmemBytes = kF2OffBar + 256;
+constexpr int kF2NW = 16;                                     // epilogue warps
+constexpr int kF2Threads = kCtrlThreads + kF2NW * 32;
+
+struct F2Bars {
+  uint64_t w_full[kWSlots], w_empty[kWSlots], acc_full[2], a_full[2], s_free[2];
+  uint32_t tmem;
+};
+static_assert(sizeof(F2Bars) <= 256, "barrier block overflows its reservation");
+
+struct PeEntry {
+  float mult;
+  int32_t code;   // dim | kind << 4 ; kind: 0 zero, 1 identity, 2 sin, 3 cos
+};
+
+__device__ __forceinline__ float pe_eval(const float (&xv)[4], PeEntry e) {
+  const int dim = e.code & 15, kind = e.code >> 4;
+  const float xs = dim == 0 ? xv[0] : (dim == 1 ? xv[1] : (dim == 2 ? xv[2] : xv[3]));
+  const float arg = xs * e.mult;
+  return kind == 1 ? xs : (kind == 2 ? __sinf(arg) : (kind == 3 ? __cosf(arg) : 0.f));
+}
+
+// log2(1 + u) = u q(u), u in [0, 1]; minimax fit (max abs error 1.03e-4)
+constexpr float kL2pC1 = 1.4390146732330322f, kL2pC2 = -0.6799439787864685f, kL2pC3 = 0.32559555768966675f,
+                kL2pC4 = -0.08476857841014862f;
+// Softplus(beta=100)(z) * scale from t = 100 z log2(e): c = ln2/100 * scale.  torch's threshold (20) needs no branch:
+// for 100 z > 20 the correction term is < 2.1e-9 * c and vanishes in the fp16 rounding of the result.
+__device__ __forceinline__ float softplus_t(float t, float c) {
+  const float u = ex2_approx(-fabsf(t));
+  float q = fmaf(kL2pC4, u, kL2pC3);
+  q = fmaf(q, u, kL2pC2);
+  q = fmaf(q, u, kL2pC1);
+  return fmaf(q, u, fmaxf(t, 0.f)) * c;
+}
+
+// A chain can run on this kernel when it is a PE prologue followed by softplus / output steps that fit K <= 256
+// and either every generation of A is saved or none is.
+static bool fwd2_supports(const TcChain& ch) {
+  if (ch.prologue != PRO_PE || ch.pro_kb > kF2MaxKB || ch.pro_colsum >= 0 || ch.n_steps < 1) return false;
+  if (ch.d_in > 4 || ch.d_in * (1 + 2 * ch.n_freqs) > kF2PeCols) return false;
+  const bool save = ch.pro_save >= 0;
+  for (int s = 0; s < ch.n_steps; ++s) {
+    const TcStep& st = ch.st[s];
+    if (st.KB > kF2MaxKB || st.next_kb > kF2MaxKB || st.n_pad > 256 || st.colsum >= 0 || st.aux1 >= 0 || st.aux2 >= 0) return false;
+    if (st.epi == EP_SOFTPLUS) {
+      if (st.next_kb <= 0 || (st.save >= 0) != save) return false;
+    } else if (st.epi == EP_SDF || st.epi == EP_Y) {
+      if (st.next_kb != 0) return false;
+    } else {
+      return false;
+    }
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_constant__ TcChain ch) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem + kF2OffA;
+  uint8_t* sW = smem + kF2OffW;
+  float* btab = reinterpret_cast<float*>(smem + kF2OffBtab);
+  PeEntry* petab = reinterpret_cast<PeEntry*>(smem + kF2OffPe);
+  F2Bars* bars = reinterpret_cast<F2Bars*>(smem + kF2OffBar);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool all_save = ch.pro_save >= 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWSlots; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->acc_full[i], 1);
+      mbar_init(&bars->a_full[i], kF2NW);
+      mbar_init(&bars->s_free[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc(&bars->tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem;
+
+  // this CTA's tiles: blockIdx.x + i * gridDim.x, i < n_mine; round r works on i = 2r (slot 0) and 2r + 1 (slot 1)
+  const int n_mine = ch.n_tiles > (int)blockIdx.x ? (ch.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int n_rounds = (n_mine + 1) >> 1;
+  auto tile_of = [&](int r, int T) -> int {
+    const int i = 2 * r + T;
+    return i < n_mine ? (int)blockIdx.x + i * (int)gridDim.x : -1;
+  };
+
+  if (warp == 0) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      uint32_t seq = 0;
+      for (int r = 0; r < n_rounds; ++r)
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          const uint32_t bytes = (uint32_t)st.n_pad * 128u;
+          for (int T = 0; T < 2; ++T) {
+            if (tile_of(r, T) < 0) continue;
+            for (int kb = 0; kb < st.KB; ++kb, ++seq) {
+              const int slot = seq % kWSlots;
+              const uint32_t use = seq / kWSlots;
+              mbar_wait(&bars->w_empty[slot], (use & 1) ^ 1);
+              mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
+              bulk_g2s(sW + slot * kWSlot, st.w + (size_t)kb * bytes, bytes, &bars->w_full[slot]);
+            }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t seq = 0, a_par = 0;
+      for (int r = 0; r < n_rounds; ++r)
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
+          for (int T = 0; T < 2; ++T) {
+            if (tile_of(r, T) < 0) continue;
+            mbar_wait(&bars->a_full[T], (a_par >> T) & 1);
+            a_par ^= 1u << T;
+            tc_fence_after();
+            const uint32_t acc = tmem + (uint32_t)T * 256u;
+            for (int kb = 0; kb < st.KB; ++kb, ++seq) {
+              const int slot = seq % kWSlots;
+              const uint32_t use = seq / kWSlots;
+              mbar_wait(&bars->w_full[slot], use & 1);
+              tc_fence_after();
+              const uint32_t a0 = smem_u32(sA + (T * kF2MaxKB + kb) * kBlk), b0 = smem_u32(sW + slot * kWSlot);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_f16(acc, make_smem_desc(a0 + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
+              umma_commit(&bars->w_empty[slot]);
+            }
+            umma_commit(&bars->acc_full[T]);
+          }
+        }
+    }
+  } else if (warp == 3) {
+    // ===== store lane: saves every generation of A_T (training forward) =====
+    if (lane == 0 && all_save) {
+      uint32_t a_par = 0;
+      for (int r = 0; r < n_rounds; ++r) {
+        for (int g = 0; g < ch.n_steps; ++g) {   // generation 0: the prologue's A ; generation g: A' of step g - 1
+          const int kbs = g == 0 ? ch.pro_kb : ch.st[g - 1].next_kb;
+          const int id = g == 0 ? ch.pro_save : ch.st[g - 1].save;
+          for (int T = 0; T < 2; ++T) {
+            const int t = tile_of(r, T);
+            if (t < 0) continue;
+            mbar_wait(&bars->a_full[T], (a_par >> T) & 1);
+            a_par ^= 1u << T;
+            if (kbs > 0 && id >= 0) {
+              bulk_s2g(ch.img[id].base + (size_t)t * ch.img[id].tile_bytes, sA + T * kF2MaxKB * kBlk, (uint32_t)kbs * kBlk);
+              bulk_commit();
+              bulk_wait_read<0>();
+              mbar_arrive(&bars->s_free[T]);
+            }
+          }
+        }
+      }
+      bulk_wait_all<0>();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue warps: TMEM lane quarter q, 16-column pieces pc = cg (mod 4) =====
+    const int ew = warp - 4, q = ew & 3, cg = ew >> 2;
+    const int m = q * 32 + lane;
+    const int et = threadIdx.x - kCtrlThreads;
+    const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
+    // bias table (softplus steps: pre-multiplied by 100 log2 e) and PE column table
+    for (int s = 0; s < ch.n_steps; ++s) {
+      const float* b = ch.st[s].bias;
+      const int nv = ch.st[s].n_valid;
+      const float mul = ch.st[s].epi == EP_SOFTPLUS ? kSpK1 : 1.0f;
+      if (et < 256) btab[s * 256 + et] = (b && et < nv) ? b[et] * mul : 0.f;
+    }
+    if (et < kF2PeCols) {
+      PeEntry e{0.f, 0};
+      const int c = et, d_in = ch.d_in;
+      if (c < d_in) {
+        e.mult = 1.f;
+        e.code = c | (1 << 4);
+      } else if (c < pe_w) {
+        const int t = c - d_in, k = t / (2 * d_in), rem = t - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
+        e.mult = (float)(1 << k);
+        e.code = dim | ((fn ? 3 : 2) << 4);
+      }
+      petab[c] = e;
+    }
+    named_bar_sync(1, kF2NW * 32);
+
+    uint32_t acc_par = 0, sf_par = 0;
+    for (int r = 0; r < n_rounds; ++r) {
+      float xv[2][4];
+      bool live[2];
+      int64_t pt[2];
+      // ---------------- prologue: A_T = PE(x) ----------------
+#pragma unroll
+      for (int T = 0; T < 2; ++T) {
+        const int t = tile_of(r, T);
+        pt[T] = (int64_t)(t < 0 ? 0 : t) * kTile + m;
+        live[T] = t >= 0 && pt[T] < ch.P;
+        xv[T][0] = xv[T][1] = xv[T][2] = xv[T][3] = 0.f;
+        if (t < 0) continue;
+        if (live[T]) {
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            if (d < ch.d_in) xv[T][d] = ch.x[pt[T] * ch.d_in + d];
+        }
+        if (all_save) {
+          mbar_wait(&bars->s_free[T], ((sf_par >> T) & 1) ^ 1);
+          sf_par ^= 1u << T;
+        }
+        uint8_t* A = sA + T * kF2MaxKB * kBlk;
+        for (int pc = cg; pc < ch.pro_kb * 4; pc += 4) {
+          float v[16];
+          const int c0 = pc * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_eval(xv[T], petab[c0 + i]) : 0.f;
+          st_row16(A + (pc >> 2) * kBlk, m, pc & 3, v);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->a_full[T]);
+      }
+
+      // ---------------- steps ----------------
+      for (int s = 0; s < ch.n_steps; ++s) {
+        const TcStep st = ch.st[s];
+        const float* btab_s = btab + s * 256;
+        const bool writes_a = st.next_kb > 0;
+        const bool last = s + 1 == ch.n_steps;
+        const float csp = kSpK2 * st.scale;
+        const int npc = max((st.n_pad + 15) >> 4, st.next_kb * 4);
+#pragma unroll
+        for (int T = 0; T < 2; ++T) {
+          if (tile_of(r, T) < 0) continue;
+          const int64_t p = pt[T];
+          uint8_t* A = sA + T * kF2MaxKB * kBlk;
+          const uint32_t tm_acc = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)T * 256u;
+          mbar_wait(&bars->acc_full[T], (acc_par >> T) & 1);
+          acc_par ^= 1u << T;
+          tc_fence_after();
+          uint32_t rr[16];
+          if (cg * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(cg * 16), rr);
+          if (writes_a && all_save) {   // the bulk store of the previous generation of A_T has read the tile
+            mbar_wait(&bars->s_free[T], ((sf_par >> T) & 1) ^ 1);
+            sf_par ^= 1u << T;
+          }
+          for (int pc = cg; pc < npc; pc += 4) {
+            const int col0 = pc * 16;
+            float acc[16];
+            if (col0 < st.n_pad) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rr[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            }
+            if (col0 + 64 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + 64), rr);
+            if (st.epi == EP_SOFTPLUS) {
+              float o[16];
+              if (col0 + 16 <= st.n_valid) {
+                const float4* b4 = reinterpret_cast<const float4*>(btab_s + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float4 b = b4[i];
+                  o[4 * i + 0] = softplus_t(fmaf(acc[4 * i + 0], kSpK1, b.x), csp);
+                  o[4 * i + 1] = softplus_t(fmaf(acc[4 * i + 1], kSpK1, b.y), csp);
+                  o[4 * i + 2] = softplus_t(fmaf(acc[4 * i + 2], kSpK1, b.z), csp);
+                  o[4 * i + 3] = softplus_t(fmaf(acc[4 * i + 3], kSpK1, b.w), csp);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = col0 + i;
+                  float v = 0.f;
+                  if (n < st.n_valid) v = softplus_t(fmaf(acc[i], kSpK1, btab_s[n & 255]), csp);
+                  else if ((st.flags & TC_PEFILL) && n - st.n_valid < pe_w) v = pe_eval(xv[T], petab[n - st.n_valid]) * st.scale;
+                  o[i] = v;
+                }
+              }
+              st_row16(A + (pc >> 2) * kBlk, m, pc & 3, o);
+            } else if (st.epi == EP_SDF) {
+              if (col0 == 0 && live[T]) {
+                float y0 = acc[0] + btab_s[0];
+                if (ch.radius > 0.f && p < ch.n_clamped) {
+                  // coordinates beyond d_in are zero
+                  const float n2 = xv[T][0] * xv[T][0] + xv[T][1] * xv[T][1] + xv[T][2] * xv[T][2] + xv[T][3] * xv[T][3];
+                  y0 = fminf(y0, ch.sph_scale * (ch.radius - sqrtf(n2)));
+                }
+                ch.sdf[p] = y0;
+              }
+            } else {   // EP_Y
+              if (live[T]) {
+                float* dst = ch.y + p * ch.ldy + st.y_col + col0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (col0 + i < st.n_valid) dst[i] = acc[i] + btab_s[(col0 + i) & 255];
+              }
+            }
+          }
+          if (!last) {
+            // A_T rewritten and / or acc_T drained: the next step's MMAs of this tile may go
+            if (writes_a) fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a_full[T]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+static int launch_fwd2(const TcChain& ch, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes));
+    attr_set = true;
+  }
+  tc_fwd2_kernel<<<grid, kF2Threads, kF2SmemBytes, st>>>(ch);
+  return SVS_OK;
+}
+
+}  // namespace tc
+}  // namespace svs

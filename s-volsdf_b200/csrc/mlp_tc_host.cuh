@@ -2,7 +2,27 @@
 // Included by mlp.cu after its `Layout` helpers.  Reference semantics: volsdf/model/network.py:71-123,170-190.
 #pragma once
 #include "mlp_tc.cuh"
+
+#ifndef SVS_TC_NW_FWD
+#define SVS_TC_NW_FWD 16
+#endif
+#ifndef SVS_TC_NW_RFWD
+#define SVS_TC_NW_RFWD 16
+#endif
+#ifndef SVS_TC_NW_REV
+#define SVS_TC_NW_REV 16
+#endif
+#ifndef SVS_TC_NW_RBWD
+#define SVS_TC_NW_RBWD 16
+#endif
+#ifndef SVS_TC_NW_TAN
+#define SVS_TC_NW_TAN 16
+#endif
+#ifndef SVS_TC_NW_BWD
+#define SVS_TC_NW_BWD 16
+#endif
 #include "mlp_tc_dw.cuh"
+#include "mlp_tc_fwd2.cuh"
 
 namespace svs {
 namespace tc {
@@ -266,16 +286,20 @@ static int num_sms() {
   return n;
 }
 
-template <uint32_t EPI, int PRO>
+template <uint32_t EPI, int PRO, int NW>
 static int launch_chain_t(const TcChain& ch, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SVS_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    SVS_CUDA_OK(cudaFuncSetAttribute(tc_chain_kernel<EPI, PRO, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  tc_chain_kernel<EPI, PRO><<<grid, kThreads, kSmemBytes, st>>>(ch);
+  tc_chain_kernel<EPI, PRO, NW><<<grid, kCtrlThreads + NW * 32, kSmemBytes, st>>>(ch);
   return SVS_OK;
 }
+
+// epilogue warps per chain: 24 where the epilogue fits 72 registers without spilling (forward nets), else 16
+constexpr int kNwFwd = SVS_TC_NW_FWD, kNwRev = SVS_TC_NW_REV, kNwRenderFwd = SVS_TC_NW_RFWD, kNwRenderBwd = SVS_TC_NW_RBWD,
+              kNwTan = SVS_TC_NW_TAN, kNwBwd = SVS_TC_NW_BWD;
 
 static int launch_chain(TcChain& ch, const char* name, double flops, double bytes, cudaStream_t st) {
   ch.n_tiles = (int)n_tiles_of(ch.P);
@@ -283,12 +307,17 @@ static int launch_chain(TcChain& ch, const char* name, double flops, double byte
   const int grid = ch.n_tiles < num_sms() ? ch.n_tiles : num_sms();
   ProfScope ps(name, flops, bytes, st);
   switch (ch.prologue) {
-    case PRO_PE: SVS_TRY((launch_chain_t<kEpiFwd, PRO_PE>(ch, grid, st))); break;
-    case PRO_LOAD_ULAST: SVS_TRY((launch_chain_t<kEpiRev, PRO_LOAD_ULAST>(ch, grid, st))); break;
-    case PRO_RENDER_IN: SVS_TRY((launch_chain_t<kEpiRenderFwd, PRO_RENDER_IN>(ch, grid, st))); break;
-    case PRO_SIGMOID_BWD: SVS_TRY((launch_chain_t<kEpiRenderBwd, PRO_SIGMOID_BWD>(ch, grid, st))); break;
-    case PRO_PE_JVP: SVS_TRY((launch_chain_t<kEpiTan, PRO_PE_JVP>(ch, grid, st))); break;
-    case PRO_DY: SVS_TRY((launch_chain_t<kEpiBwd, PRO_DY>(ch, grid, st))); break;
+    case PRO_PE:
+#ifndef SVS_TC_NO_FWD2
+      if (fwd2_supports(ch)) { SVS_TRY(launch_fwd2(ch, grid, st)); break; }   // two tiles in flight (mlp_tc_fwd2.cuh)
+#endif
+      SVS_TRY((launch_chain_t<kEpiFwd, PRO_PE, kNwFwd>(ch, grid, st)));
+      break;
+    case PRO_LOAD_ULAST: SVS_TRY((launch_chain_t<kEpiRev, PRO_LOAD_ULAST, kNwRev>(ch, grid, st))); break;
+    case PRO_RENDER_IN: SVS_TRY((launch_chain_t<kEpiRenderFwd, PRO_RENDER_IN, kNwRenderFwd>(ch, grid, st))); break;
+    case PRO_SIGMOID_BWD: SVS_TRY((launch_chain_t<kEpiRenderBwd, PRO_SIGMOID_BWD, kNwRenderBwd>(ch, grid, st))); break;
+    case PRO_PE_JVP: SVS_TRY((launch_chain_t<kEpiTan, PRO_PE_JVP, kNwTan>(ch, grid, st))); break;
+    case PRO_DY: SVS_TRY((launch_chain_t<kEpiBwd, PRO_DY, kNwBwd>(ch, grid, st))); break;
     default: set_error("launch_chain: unknown prologue %d", ch.prologue); return SVS_ERR_INVALID;
   }
   SVS_LAUNCH_OK();
