@@ -5,6 +5,7 @@
 //
 // Reference: density.py:21-35, network.py:281-295 (volume_rendering), :239-248 (rgb/depth),
 // :270-276 (normal map), network_bg.py:147-180 (fg tail + bg pass).  Math of the backward: SURVEY.md App. G.
+#include <map>
 #include <type_traits>
 
 #include "svs_common.cuh"
@@ -13,13 +14,59 @@ namespace svs {
 
 constexpr int kCompWarps = 4;
 
+// per-warp input rows of one ray (z has one pad element for the i + 1 access); `g` is the normals row (forward, eval)
+// or the dL/dweights row (backward)
+template <int C>
+struct CompRows {
+  float z[32 * C + 4];
+  float s[32 * C];
+  float c[32 * C * 3];
+  float g[32 * C * 3];
+};
+// two stages per warp: the rows of the warp's NEXT ray land (cp.async, no registers) while the current ray is being
+// composited, so a warp's HBM latency overlaps its own arithmetic; + one output row
 template <int C>
 struct CompSmem {
-  float z[kCompWarps][32 * C + 1];
-  float s[kCompWarps][32 * C];
+  CompRows<C> in[kCompWarps][2];
   float w[kCompWarps][32 * C];
-  float c[kCompWarps][32 * C * 3];
+  float o[kCompWarps][32 * C];
 };
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// issue the asynchronous copies of one ray's rows (coalesced 4-byte elements: the rows are only 4-byte aligned)
+template <int C>
+__device__ __forceinline__ void issue_rows(CompRows<C>& st, const float* __restrict__ zr, const float* __restrict__ sr,
+                                           const float* __restrict__ cr, const float* __restrict__ gr, int n_g, int S, int lane) {
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int i = lane + 32 * j;
+    if (i < S) {
+      cp_async4(st.z + i, zr + i);
+      cp_async4(st.s + i, sr + i);
+    }
+  }
+  if (cr) {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) {
+      const int i = lane + 32 * j;
+      if (i < 3 * S) cp_async4(st.c + i, cr + i);
+    }
+  }
+  if (gr) {
+#pragma unroll
+    for (int j = 0; j < 3 * C; ++j) {
+      const int i = lane + 32 * j;
+      if (i < n_g) cp_async4(st.g + i, gr + i);
+    }
+  }
+  cp_async_commit();
+}
 
 __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min) {
   return fabsf(__ldg(beta_param)) + beta_min;  // density.py:28-30
@@ -30,48 +77,6 @@ __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min
 // 5-8 % — the kernels are bound by per-ray instruction count, not by the transcendentals.
 template <bool FAST>
 __device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
-
-// Coalesced staging of a ray's rows into shared memory.  All global loads are issued before the first shared store
-// (registers in between), so a warp keeps C + C + 3C independent 128-byte requests in flight: with one request at a
-// time per warp the kernels reached only a quarter of the HBM bandwidth (latency-bound, profiles/r1_hbm_kernels.json).
-template <int N>
-__device__ __forceinline__ void stage_row(const float* __restrict__ src, int n, int lane, float* dst) {
-  float r[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const int i = lane + 32 * j;
-    r[j] = (i < n) ? __ldg(src + i) : 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < N; ++j) dst[lane + 32 * j] = r[j];
-}
-template <int C>
-__device__ __forceinline__ void stage_rows(const float* __restrict__ zr, const float* __restrict__ sr,
-                                           const float* __restrict__ cr, int S, int lane, float* dz, float* dsd, float* dc) {
-  float rz[C], rs[C], rc[3 * C];
-#pragma unroll
-  for (int j = 0; j < C; ++j) {
-    const int i = lane + 32 * j;
-    rz[j] = (i < S) ? __ldg(zr + i) : 0.f;
-    rs[j] = (i < S) ? __ldg(sr + i) : 0.f;
-  }
-  if (cr) {
-#pragma unroll
-    for (int j = 0; j < 3 * C; ++j) {
-      const int i = lane + 32 * j;
-      rc[j] = (i < 3 * S) ? __ldg(cr + i) : 0.f;
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < C; ++j) {
-    dz[lane + 32 * j] = rz[j];
-    dsd[lane + 32 * j] = rs[j];
-  }
-  if (cr) {
-#pragma unroll
-    for (int j = 0; j < 3 * C; ++j) dc[lane + 32 * j] = rc[j];
-  }
-}
 
 // sigma and the autograd-form derivative d sigma / d s
 template <bool FAST = false>
@@ -119,31 +124,57 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
                      int flags, float* __restrict__ weights, float* __restrict__ rgb_values,
                      float* __restrict__ depth_values, float* __restrict__ normal_map,
                      float* __restrict__ bg_trans) {
-  __shared__ CompSmem<C> sm;
+  extern __shared__ __align__(16) uint8_t comp_smem_raw[];
+  CompSmem<C>& sm = *reinterpret_cast<CompSmem<C>*>(comp_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
              tail = flags & SVS_COMP_ZMAX_TAIL;
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
-  for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
-    stage_rows<C>(z + ray * S, sdf + ray * S, rgb ? rgb + ray * S * 3 : nullptr, S, lane, sm.z[warp], sm.s[warp], sm.c[warp]);
-    if (lane == 0) sm.z[warp][32 * C] = 0.f;
+  const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
+  // rows shorter than the padded width read as zeros: the copies never touch the pad
+  for (int k = 0; k < 2; ++k) {
+    CompRows<C>& st = sm.in[warp][k];
+    for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
+    for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
+  }
+  __syncwarp();
+  const float* nrm_rows = normal_map ? normals : nullptr;
+  if (ray0 < R)
+    issue_rows<C>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
+                  nrm_rows ? nrm_rows + ray0 * S * 3 : nullptr, 3 * S, S, lane);
+  float n_ds = (depth_scale && ray0 < R) ? __ldg(depth_scale + ray0) : 1.f;
+  float n_zmax = (tail && ray0 < R) ? __ldg(z_max + ray0) : 0.f;
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k ^= 1) {
+    const float ds = n_ds, zmax = n_zmax;
+    const int64_t nxt = ray + stride;
+    if (nxt < R) {   // the next ray's rows and per-ray scalars are in flight while this ray is composited
+      issue_rows<C>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
+                    nrm_rows ? nrm_rows + nxt * S * 3 : nullptr, 3 * S, S, lane);
+      if (depth_scale) n_ds = __ldg(depth_scale + nxt);
+      if (tail) n_zmax = __ldg(z_max + nxt);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncwarp();
+    const CompRows<C>& in = sm.in[warp][k];
     using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C];
     ScanT excl[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float zi = sm.z[warp][i];
+      float zi = in.z[i];
       zz[j] = zi;
       float em;
-      float sigma = density_fwd<FAST>(sm.s[warp][i], beta, abs_d, &em);
+      float sigma = density_fwd<FAST>(in.s[i], beta, abs_d, &em);
       float d;
       if (i < S - 1) {
-        float zn = sm.z[warp][i + 1];
+        float zn = in.z[i + 1];
         d = rev ? (zi - zn) : (zn - zi);
       } else if (i == S - 1) {
-        d = tail ? (__ldg(z_max + ray) - zi) : 1e10f;
+        d = tail ? (zmax - zi) : 1e10f;
       } else {
         d = 0.f;
       }
@@ -162,9 +193,9 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
         acc_w += w;
         acc_wz += w * zz[j];
         if (rgb) {
-          acc_r += w * sm.c[warp][3 * i];
-          acc_g += w * sm.c[warp][3 * i + 1];
-          acc_b += w * sm.c[warp][3 * i + 2];
+          acc_r += w * in.c[3 * i];
+          acc_g += w * in.c[3 * i + 1];
+          acc_b += w * in.c[3 * i + 2];
         }
       }
     }
@@ -179,11 +210,8 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     }
     float nr = 0.f, ng = 0.f, nb = 0.f;
     if (normal_map) {  // eval: sum w * g/|g|  (network.py:270-274; no eps, as the reference)
-      __syncwarp();
-      stage_row<3 * C>(normals + ray * S * 3, S * 3, lane, sm.c[warp]);
-      __syncwarp();
       for (int i = lane; i < S; i += 32) {
-        float gx = sm.c[warp][3 * i], gy = sm.c[warp][3 * i + 1], gz = sm.c[warp][3 * i + 2];
+        float gx = in.g[3 * i], gy = in.g[3 * i + 1], gz = in.g[3 * i + 2];
         float n = sqrtf(gx * gx + gy * gy + gz * gz);
         float w = sm.w[warp][i];
         nr += w * (gx / n);
@@ -201,7 +229,6 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
         rgb_values[ray * 3 + 2] = acc_b;
       }
       if (depth_values) {
-        float ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
         depth_values[ray] = ds * (acc_wz / (acc_w + 1e-8f));
       }
       if (normal_map) {
@@ -223,38 +250,70 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
                      int flags, const float* __restrict__ d_rgb_values, const float* __restrict__ d_depth_values,
                      const float* __restrict__ d_weights, const float* __restrict__ d_bg_trans,
                      float* __restrict__ d_sdf, float* __restrict__ d_rgb, float* __restrict__ d_beta_param) {
-  __shared__ CompSmem<C> sm;
+  extern __shared__ __align__(16) uint8_t comp_smem_raw[];
+  CompSmem<C>& sm = *reinterpret_cast<CompSmem<C>*>(comp_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
              tail = flags & SVS_COMP_ZMAX_TAIL;
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
   float dbeta_acc = 0.f;
-  for (int64_t ray = blockIdx.x * (int64_t)kCompWarps + warp; ray < R; ray += (int64_t)gridDim.x * kCompWarps) {
-    stage_rows<C>(z + ray * S, sdf + ray * S, rgb ? rgb + ray * S * 3 : nullptr, S, lane, sm.z[warp], sm.s[warp], sm.c[warp]);
-    if (d_weights) stage_row<C>(d_weights + ray * S, S, lane, sm.w[warp]);
+  const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
+  for (int k = 0; k < 2; ++k) {
+    CompRows<C>& st = sm.in[warp][k];
+    for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
+    for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
+  }
+  __syncwarp();
+  // per-ray scalars of the NEXT ray are fetched together with its rows
+  struct RayScal { float gr, gg, gb, gdep, gbt, ds, zmax; };
+  auto load_scal = [&](int64_t ray) {
+    RayScal q;
+    q.gr = d_rgb_values ? __ldg(d_rgb_values + ray * 3) : 0.f;
+    q.gg = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 1) : 0.f;
+    q.gb = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 2) : 0.f;
+    q.gdep = d_depth_values ? __ldg(d_depth_values + ray) : 0.f;
+    q.gbt = (tail && d_bg_trans) ? __ldg(d_bg_trans + ray) : 0.f;
+    q.ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
+    q.zmax = tail ? __ldg(z_max + ray) : 0.f;
+    return q;
+  };
+  RayScal nq = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+  if (ray0 < R) {
+    issue_rows<C>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
+                  d_weights ? d_weights + ray0 * S : nullptr, S, S, lane);
+    nq = load_scal(ray0);
+  }
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k ^= 1) {
+    const RayScal cq = nq;
+    const int64_t nxt = ray + stride;
+    if (nxt < R) {
+      issue_rows<C>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
+                    d_weights ? d_weights + nxt * S : nullptr, S, S, lane);
+      nq = load_scal(nxt);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncwarp();
-    const float gr = d_rgb_values ? __ldg(d_rgb_values + ray * 3) : 0.f;
-    const float gg = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 1) : 0.f;
-    const float gb = d_rgb_values ? __ldg(d_rgb_values + ray * 3 + 2) : 0.f;
-    const float gdep = d_depth_values ? __ldg(d_depth_values + ray) : 0.f;
-    const float gbt = (tail && d_bg_trans) ? __ldg(d_bg_trans + ray) : 0.f;
-    const float ds = depth_scale ? __ldg(depth_scale + ray) : 1.f;
+    const CompRows<C>& in = sm.in[warp][k];
+    const float gr = cq.gr, gg = cq.gg, gb = cq.gb, gdep = cq.gdep, gbt = cq.gbt, ds = cq.ds;
     using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C], dl[C], sig[C], em[C], ss[C];
     ScanT excl[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float zi = sm.z[warp][i];
+      float zi = in.z[i];
       zz[j] = zi;
-      ss[j] = sm.s[warp][i];
+      ss[j] = in.s[i];
       sig[j] = density_fwd<FAST>(ss[j], beta, abs_d, &em[j]);
       float d;
       if (i < S - 1) {
-        float zn = sm.z[warp][i + 1];
+        float zn = in.z[i + 1];
         d = rev ? (zi - zn) : (zn - zi);
       } else if (i == S - 1) {
-        d = tail ? (__ldg(z_max + ray) - zi) : 1e10f;
+        d = tail ? (cq.zmax - zi) : 1e10f;
       } else {
         d = 0.f;
       }
@@ -284,14 +343,13 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       int i = lane * C + j;
       float v = 0.f;
       if (i < S) {
-        if (rgb) v = sm.c[warp][3 * i] * gr + sm.c[warp][3 * i + 1] * gg + sm.c[warp][3 * i + 2] * gb;
-        if (d_weights) v += sm.w[warp][i];
+        if (rgb) v = in.c[3 * i] * gr + in.c[3 * i + 1] * gg + in.c[3 * i + 2] * gb;
+        if (d_weights) v += in.g[i];
         v += gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
       }
       what[j] = v;
       ww[j] = v * w[j];
     }
-    __syncwarp();   // sm.w (staged dL/dweights) is rewritten with w below
     // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
     ScanT excl2[C];
     ScanT tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);
@@ -314,13 +372,13 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
           dsdf = -dsig * nz * e / (2.0f * beta * beta);
           dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
         }
-        sm.s[warp][i] = dsdf;   // every lane has its sdf values in registers: reuse the row for the coalesced store
+        sm.o[warp][i] = dsdf;   // rows leave through shared memory: coalesced stores
         sm.w[warp][i] = w[j];
       }
     }
     dbeta_acc += dbeta;
     __syncwarp();
-    for (int i = lane; i < S; i += 32) d_sdf[ray * S + i] = sm.s[warp][i];
+    for (int i = lane; i < S; i += 32) d_sdf[ray * S + i] = sm.o[warp][i];
     if (d_rgb) {
       float* o = d_rgb + ray * S * 3;
       for (int i = lane; i < S * 3; i += 32) {
@@ -380,9 +438,20 @@ __global__ void density_bwd_kernel(const float* __restrict__ sdf, int64_t n, int
   }
 }
 
-static int comp_grid(int64_t R) {
-  int64_t blocks = cdiv(R, kCompWarps);
-  int64_t cap = (int64_t)kNumSMs * 16;
+// one wave of resident CTAs (grid-stride over rays): a warp's next-ray prefetch then always has a successor
+template <typename K>
+static int comp_grid(K kernel, size_t smem, int64_t R) {
+  static std::map<const void*, int> resident;   // kernel -> CTAs of one wave (attribute + occupancy queried once)
+  int& cap_ctas = resident[(const void*)kernel];
+  if (cap_ctas == 0) {
+    int per_sm = 0, sms = 0, dev = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCompWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = kNumSMs;
+    cap_ctas = sms * per_sm;
+  }
+  const int64_t blocks = cdiv(R, kCompWarps), cap = cap_ctas;
   return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -411,11 +480,11 @@ extern "C" int svs_composite_forward(const float* z, const float* sdf, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_fwd", 0.0, (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (normal_map ? 3 : 0)) + 32), st);
   if (flags & SVS_COMP_FAST) {
-    DISPATCH_C(S, (composite_fwd_kernel<C, true><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+    DISPATCH_C(S, (composite_fwd_kernel<C, true><<<comp_grid(composite_fwd_kernel<C, true>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
                       z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
                       rgb_values, depth_values, normal_map, bg_trans)));
   } else {
-    DISPATCH_C(S, (composite_fwd_kernel<C, false><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+    DISPATCH_C(S, (composite_fwd_kernel<C, false><<<comp_grid(composite_fwd_kernel<C, false>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
                       z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
                       rgb_values, depth_values, normal_map, bg_trans)));
   }
@@ -439,11 +508,11 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   ProfScope ps("composite_bwd", 0.0,
                (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (d_weights ? 1 : 0) + (d_rgb ? 3 : 0)) + 32), st);
   if (flags & SVS_COMP_FAST) {
-    DISPATCH_C(S, (composite_bwd_kernel<C, true><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+    DISPATCH_C(S, (composite_bwd_kernel<C, true><<<comp_grid(composite_bwd_kernel<C, true>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
                       z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                       d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
   } else {
-    DISPATCH_C(S, (composite_bwd_kernel<C, false><<<comp_grid(R), kCompWarps * 32, 0, st>>>(
+    DISPATCH_C(S, (composite_bwd_kernel<C, false><<<comp_grid(composite_bwd_kernel<C, false>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
                       z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                       d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
   }

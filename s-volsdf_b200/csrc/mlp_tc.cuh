@@ -282,6 +282,7 @@ template <uint32_t EPI, int PRO, int NW>
 __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(const __grid_constant__ TcChain ch) {
   constexpr int kThreads = kCtrlThreads + NW * 32, kEpiThreads = NW * 32, NCG = NW / 4;   // NCG column groups
   static_assert(NW % 4 == 0 && NCG >= 4, "every block needs 4 distinct column groups");
+  static_assert(NW == 16 || (PRO != PRO_DY && (EPI & epi_bit(EP_DFEAT)) == 0), "row-ownership passes assume 16 epilogue warps x 8 rows");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem + kOffA;
   uint8_t* sW = smem + kOffW;
@@ -504,7 +505,67 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         mbar_wait(&bars->a_load, n_load & 1);
         ++n_load;
       }
-      for (int pc = cg; pc < ch.pro_kb * 4; pc += NCG) {
+      if (PRO == PRO_DY) {
+        // dy is fp32 row-major (P x ldy): warp ew converts rows 8 ew .. 8 ew + 7, a lane reads columns lane, lane + 32,
+        // ... (one 128-byte line per instruction); column 0 (which also takes w * dL/dsdf) is written by the thread
+        // that owns the row.  The pieces are published after all warps are done.
+        for (int b = 0; b < ch.pro_kb; ++b) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
+        const int64_t trow0 = (int64_t)t * kTile;
+        const int ncol = ch.pro_kb * 64;
+        float csum[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) csum[j] = 0.f;
+        for (int rb = 0; rb < 8; rb += 2) {
+          float fv[2][10];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int64_t pr = trow0 + ew * 8 + rb + h;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+              const int c = lane + 32 * j;
+              fv[h][j] = (ch.dy && pr < ch.P && c >= 1 && c < ch.dy_cols) ? __ldg(ch.dy + pr * ch.ldy + c) * gs : 0.f;
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int row = ew * 8 + rb + h;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+              const int c = lane + 32 * j;
+              if (c >= 1 && c < ncol) {
+                csum[j] += fv[h][j];
+                *reinterpret_cast<__half*>(sA + (c >> 6) * kBlk + chunk_off(row, (c & 63) >> 3) + (c & 7) * 2) =
+                    __float2half_rn(fminf(fmaxf(fv[h][j], -65504.f), 65504.f));
+              }
+            }
+          }
+        }
+        float v0 = 0.f;
+        if (cg == 0) {   // one thread per row
+          if (live) {
+            if (ch.dy) v0 = ch.dy[p * ch.ldy];
+            if (ch.d_sdf) v0 += cw * ch.d_sdf[p];
+            v0 *= gs;
+          }
+          *reinterpret_cast<__half*>(sA + chunk_off(m, 0)) = __float2half_rn(fminf(fmaxf(v0, -65504.f), 65504.f));
+        }
+        if (ch.pro_colsum >= 0) {
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            const int c = lane + 32 * j;
+            if (c >= 1 && c < ch.dy_cols) atomicAdd(&colsum[ch.pro_colsum * kColsumW + c], csum[j]);
+          }
+          if (cg == 0) {
+            const float s0 = warp_sum(v0);
+            if (lane == 0) atomicAdd(&colsum[ch.pro_colsum * kColsumW], s0);
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, kEpiThreads);
+        if (lane == 0)
+          for (int pc = cg; pc < ch.pro_kb * 4; pc += NCG) mbar_arrive(&bars->a_ready[pc]);
+      }
+      for (int pc = cg; PRO != PRO_DY && pc < ch.pro_kb * 4; pc += NCG) {
         float v[16];
         const int b = pc >> 2, cq = pc & 3;
         const int c0 = pc * 16;
@@ -739,11 +800,26 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
               for (int i = 0; i < 16; ++i) o[i] = (h_elem(a1, i) > 0.f && col0 + i < st.n_valid) ? acc[i] : 0.f;
             }
           } else if ((EPI & epi_bit(EP_DFEAT)) && st.epi == EP_DFEAT) {
-            if (live && ch.d_feat) {
-              float* dst = ch.d_feat + p * ch.ld_dfeat + col0;
+            if (ch.d_feat) {
+              // fp32 row-major output from a thread-per-row register layout: transposed through this warp's scratch
+              // (the stash region is idle in this chain) so that one store instruction writes 4 rows x 8 contiguous
+              // floats instead of 32 rows x 1
+              float* scr = stash + ew * 288;
+              const int64_t row0 = (int64_t)t * kTile + q * 32;
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + i < st.n_valid) dst[i] = acc[i] * inv_gs;
+              for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) scr[lane * 9 + i] = acc[hf * 8 + i] * inv_gs;
+                __syncwarp();
+                const int cc = lane & 7, n = col0 + hf * 8 + cc;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const int rw = 4 * k + (lane >> 3);
+                  const int64_t pr = row0 + rw;
+                  if (pr < ch.P && n < st.n_valid) ch.d_feat[pr * ch.ld_dfeat + n] = scr[rw * 9 + cc];
+                }
+                __syncwarp();
+              }
             }
           } else if ((EPI & epi_bit(EP_DSMALL)) && st.epi == EP_DSMALL) {
             if (live && ch.d_normals) {
@@ -878,6 +954,7 @@ constexpr uint32_t kEpiFwd = epi_bit(EP_SOFTPLUS) | epi_bit(EP_SDF) | epi_bit(EP
 constexpr uint32_t kEpiRev = epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD);
 constexpr uint32_t kEpiRenderFwd = epi_bit(EP_RELU) | epi_bit(EP_RGB);
 constexpr uint32_t kEpiRenderBwd = epi_bit(EP_RELU_BWD) | epi_bit(EP_DFEAT) | epi_bit(EP_DSMALL);
+static_assert(16 * 288 * 4 <= kTile * kStashLd * 4, "EP_DFEAT scratch must fit the stash region");
 constexpr uint32_t kEpiTan = epi_bit(EP_TANGENT);
 constexpr uint32_t kEpiBwd = epi_bit(EP_BACKWARD);
 

@@ -22,16 +22,26 @@
 namespace svs {
 namespace tc {
 
-constexpr int kF2MaxKB = 4;                                   // K <= 256
-constexpr int kF2OffA = 0;                                    // A[2][4] blocks
-constexpr int kF2OffW = 2 * kF2MaxKB * kBlk;                  // 131072
-constexpr int kF2OffBtab = kF2OffW + kWSlots * kWSlot;        // 196608
-constexpr int kF2OffPe = kF2OffBtab + kMaxSteps * 256 * 4;    // 207872 : 128 PE column entries of 8 bytes
+// MODE 0: SDF forward (K <= 256: 4 blocks per tile, bias + PE tables in shared memory)
+// MODE 1: rendering-net forward (first layer K = F + 64 = 320: 5 blocks per tile; biases come through the read-only
+//         cache because the two 80 KB tiles and the weight ring leave no room for a table)
+constexpr int kF2Sdf = 0, kF2Render = 1;
 constexpr int kF2PeCols = 128;
-constexpr int kF2OffBar = kF2OffPe + kF2PeCols * 8;           // 208896
-constexpr int kF2SmemBytes = kF2OffBar + 256;
 constexpr int kF2NW = 16;                                     // epilogue warps
 constexpr int kF2Threads = kCtrlThreads + kF2NW * 32;
+template <int MODE>
+struct F2Cfg {
+  static constexpr int kMaxKB = MODE == kF2Render ? 5 : 4;
+  static constexpr int kOffA = 0;                                          // A[2][kMaxKB] blocks
+  static constexpr int kOffW = 2 * kMaxKB * kBlk;
+  static constexpr int kOffBtab = kOffW + kWSlots * kWSlot;
+  static constexpr int kBtabBytes = MODE == kF2Render ? 0 : kMaxSteps * 256 * 4;
+  static constexpr int kOffPe = kOffBtab + kBtabBytes;                     // 128 PE column entries of 8 bytes
+  static constexpr int kPeBytes = MODE == kF2Render ? 0 : kF2PeCols * 8;
+  static constexpr int kOffBar = kOffPe + kPeBytes;
+  static constexpr int kSmemBytes = kOffBar + 256;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
+};
 
 struct F2Bars {
   uint64_t w_full[kWSlots], w_empty[kWSlots], acc_full[2], a_full[2], s_free[2];
@@ -67,15 +77,19 @@ __device__ __forceinline__ float softplus_t(float t, float c) {
 // A chain can run on this kernel when it is a PE prologue followed by softplus / output steps that fit K <= 256
 // and either every generation of A is saved or none is.
 static bool fwd2_supports(const TcChain& ch) {
-  if (ch.prologue != PRO_PE || ch.pro_kb > kF2MaxKB || ch.pro_colsum >= 0 || ch.n_steps < 1) return false;
-  if (ch.d_in > 4 || ch.d_in * (1 + 2 * ch.n_freqs) > kF2PeCols) return false;
+  const bool render = ch.prologue == PRO_RENDER_IN;
+  if (ch.prologue != PRO_PE && !render) return false;
+  const int max_kb = render ? F2Cfg<kF2Render>::kMaxKB : F2Cfg<kF2Sdf>::kMaxKB;
+  if (ch.pro_kb > max_kb || ch.pro_colsum >= 0 || ch.n_steps < 1) return false;
+  if (!render && (ch.d_in > 4 || ch.d_in * (1 + 2 * ch.n_freqs) > kF2PeCols)) return false;
+  if (render && ((ch.F & 63) != 0 || ch.F > 256 || ch.pro_kb != ch.F / 64 + 1)) return false;
   const bool save = ch.pro_save >= 0;
   for (int s = 0; s < ch.n_steps; ++s) {
     const TcStep& st = ch.st[s];
-    if (st.KB > kF2MaxKB || st.next_kb > kF2MaxKB || st.n_pad > 256 || st.colsum >= 0 || st.aux1 >= 0 || st.aux2 >= 0) return false;
-    if (st.epi == EP_SOFTPLUS) {
+    if (st.KB > max_kb || st.next_kb > max_kb || st.n_pad > 256 || st.colsum >= 0 || st.aux1 >= 0 || st.aux2 >= 0) return false;
+    if (st.epi == (render ? EP_RELU : EP_SOFTPLUS)) {
       if (st.next_kb <= 0 || (st.save >= 0) != save) return false;
-    } else if (st.epi == EP_SDF || st.epi == EP_Y) {
+    } else if (render ? st.epi == EP_RGB : (st.epi == EP_SDF || st.epi == EP_Y)) {
       if (st.next_kb != 0) return false;
     } else {
       return false;
@@ -84,13 +98,16 @@ static bool fwd2_supports(const TcChain& ch) {
   return true;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_constant__ TcChain ch) {
+  typedef F2Cfg<MODE> Cfg;
+  constexpr int kF2MaxKB = Cfg::kMaxKB;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sA = smem + kF2OffA;
-  uint8_t* sW = smem + kF2OffW;
-  float* btab = reinterpret_cast<float*>(smem + kF2OffBtab);
-  PeEntry* petab = reinterpret_cast<PeEntry*>(smem + kF2OffPe);
-  F2Bars* bars = reinterpret_cast<F2Bars*>(smem + kF2OffBar);
+  uint8_t* sA = smem + Cfg::kOffA;
+  uint8_t* sW = smem + Cfg::kOffW;
+  float* btab = reinterpret_cast<float*>(smem + Cfg::kOffBtab);
+  PeEntry* petab = reinterpret_cast<PeEntry*>(smem + Cfg::kOffPe);
+  F2Bars* bars = reinterpret_cast<F2Bars*>(smem + Cfg::kOffBar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool all_save = ch.pro_save >= 0;
@@ -197,29 +214,40 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
     const int m = q * 32 + lane;
     const int et = threadIdx.x - kCtrlThreads;
     const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
-    // bias table (softplus steps: pre-multiplied by 100 log2 e) and PE column table
-    for (int s = 0; s < ch.n_steps; ++s) {
-      const float* b = ch.st[s].bias;
-      const int nv = ch.st[s].n_valid;
-      const float mul = ch.st[s].epi == EP_SOFTPLUS ? kSpK1 : 1.0f;
-      if (et < 256) btab[s * 256 + et] = (b && et < nv) ? b[et] * mul : 0.f;
-    }
-    if (et < kF2PeCols) {
-      PeEntry e{0.f, 0};
-      const int c = et, d_in = ch.d_in;
-      if (c < d_in) {
-        e.mult = 1.f;
-        e.code = c | (1 << 4);
-      } else if (c < pe_w) {
-        const int t = c - d_in, k = t / (2 * d_in), rem = t - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
-        e.mult = (float)(1 << k);
-        e.code = dim | ((fn ? 3 : 2) << 4);
+    if constexpr (MODE == kF2Sdf) {
+      // bias table (softplus steps: pre-multiplied by 100 log2 e) and PE column table
+      for (int s = 0; s < ch.n_steps; ++s) {
+        const float* b = ch.st[s].bias;
+        const int nv = ch.st[s].n_valid;
+        const float mul = ch.st[s].epi == EP_SOFTPLUS ? kSpK1 : 1.0f;
+        if (et < 256) btab[s * 256 + et] = (b && et < nv) ? b[et] * mul : 0.f;
       }
-      petab[c] = e;
+      if (et < kF2PeCols) {
+        PeEntry e{0.f, 0};
+        const int c = et, d_in = ch.d_in;
+        if (c < d_in) {
+          e.mult = 1.f;
+          e.code = c | (1 << 4);
+        } else if (c < pe_w) {
+          const int t = c - d_in, k = t / (2 * d_in), rem = t - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
+          e.mult = (float)(1 << k);
+          e.code = dim | ((fn ? 3 : 2) << 4);
+        }
+        petab[c] = e;
+      }
+      named_bar_sync(1, kF2NW * 32);
     }
-    named_bar_sync(1, kF2NW * 32);
 
-    uint32_t acc_par = 0, sf_par = 0;
+    // s_free[T] is awaited lazily: `pend` bit T = the last generation of A_T is being saved and the bulk store may still
+    // read the tile; whoever reuses A_T next (new generation, or scratch of the y stores) waits for it first
+    uint32_t acc_par = 0, sf_par = 0, pend = 0;
+    auto a_tile_free = [&](int T) {
+      if (pend & (1u << T)) {
+        mbar_wait(&bars->s_free[T], (sf_par >> T) & 1);
+        sf_par ^= 1u << T;
+        pend &= ~(1u << T);
+      }
+    };
     for (int r = 0; r < n_rounds; ++r) {
       float xv[2][4];
       bool live[2];
@@ -232,26 +260,80 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
         live[T] = t >= 0 && pt[T] < ch.P;
         xv[T][0] = xv[T][1] = xv[T][2] = xv[T][3] = 0.f;
         if (t < 0) continue;
-        if (live[T]) {
+        if constexpr (MODE == kF2Sdf) {
+          if (live[T]) {
 #pragma unroll
-          for (int d = 0; d < 4; ++d)
-            if (d < ch.d_in) xv[T][d] = ch.x[pt[T] * ch.d_in + d];
+            for (int d = 0; d < 4; ++d)
+              if (d < ch.d_in) xv[T][d] = ch.x[pt[T] * ch.d_in + d];
+          }
         }
-        if (all_save) {
-          mbar_wait(&bars->s_free[T], ((sf_par >> T) & 1) ^ 1);
-          sf_par ^= 1u << T;
-        }
+        a_tile_free(T);
         uint8_t* A = sA + T * kF2MaxKB * kBlk;
-        for (int pc = cg; pc < ch.pro_kb * 4; pc += 4) {
-          float v[16];
-          const int c0 = pc * 16;
+        if constexpr (MODE == kF2Sdf) {
+          for (int pc = cg; pc < ch.pro_kb * 4; pc += 4) {
+            float v[16];
+            const int c0 = pc * 16;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_eval(xv[T], petab[c0 + i]) : 0.f;
-          st_row16(A + (pc >> 2) * kBlk, m, pc & 3, v);
+            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_eval(xv[T], petab[c0 + i]) : 0.f;
+            st_row16(A + (pc >> 2) * kBlk, m, pc & 3, v);
+          }
+        } else {
+          // A = [feat (F columns) | points(3) if idr, PE(view), normals(3) if idr]; this warp's pieces are cg, cg + 4, ...
+          // The feature loads of two pieces are issued together (8 x 128 bits in flight per thread).
+          // features: fp32 row-major.  Warp ew converts rows 8 ew .. 8 ew + 7: a lane reads columns lane, lane + 32, ...
+          // (one 128-byte line per instruction) and drops the fp16 value at its place in the swizzled tile.
+          const int nfp = (ch.F >> 6) * 4;   // feature pieces
+          const int64_t trow0 = pt[T] - m;   // first point of the tile
+          for (int rb = 0; rb < 8; rb += 2) {
+            float fv[2][8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int64_t pr = trow0 + ew * 8 + rb + h;
+              const float* frow = ch.feat + pr * ch.ld_feat;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                fv[h][j] = (pr < ch.P && tile_of(r, T) >= 0 && c < ch.F) ? __ldg(frow + c) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int row = ew * 8 + rb + h;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (c < ch.F) {
+                  const __half hv = __float2half_rn(fminf(fmaxf(fv[h][j], -65504.f), 65504.f));
+                  *reinterpret_cast<__half*>(A + (c >> 6) * kBlk + chunk_off(row, (c & 63) >> 3) + (c & 7) * 2) = hv;
+                }
+              }
+            }
+          }
+          {
+            // the small block: piece nfp + cg
+            const int pe_v = 3 * (1 + 2 * ch.view_freqs);
+            const int o_view = ch.idr ? 3 : 0, o_n = o_view + pe_v, n_small = o_n + (ch.idr ? 3 : 0);
+            float vv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (live[T] && cg * 16 < n_small) { vv[0] = ch.view[pt[T] * 3]; vv[1] = ch.view[pt[T] * 3 + 1]; vv[2] = ch.view[pt[T] * 3 + 2]; }
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = cg * 16 + i;
+              float rv = 0.f;
+              if (live[T] && c < n_small) {
+                if (c < o_view) rv = ch.points[pt[T] * 3 + c];
+                else if (c < o_n) rv = pe_col(vv, 3, ch.view_freqs, c - o_view);
+                else rv = ch.normals[pt[T] * 3 + (c - o_n)];
+              }
+              v[i] = rv;
+            }
+            st_row16(A + (nfp >> 2) * kBlk, m, cg, v);
+          }
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->a_full[T]);
+        if (all_save) pend |= 1u << T;
       }
 
       // ---------------- steps ----------------
@@ -273,10 +355,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
           tc_fence_after();
           uint32_t rr[16];
           if (cg * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(cg * 16), rr);
-          if (writes_a && all_save) {   // the bulk store of the previous generation of A_T has read the tile
-            mbar_wait(&bars->s_free[T], ((sf_par >> T) & 1) ^ 1);
-            sf_par ^= 1u << T;
-          }
+          // the tile is rewritten (A') or used as scratch (coalesced y stores): the bulk store that saves the previous
+          // generation must have read it
+          if (writes_a || (st.epi == EP_Y && last)) a_tile_free(T);
           for (int pc = cg; pc < npc; pc += 4) {
             const int col0 = pc * 16;
             float acc[16];
@@ -289,45 +370,88 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
               for (int i = 0; i < 16; ++i) acc[i] = 0.f;
             }
             if (col0 + 64 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + 64), rr);
-            if (st.epi == EP_SOFTPLUS) {
-              float o[16];
-              if (col0 + 16 <= st.n_valid) {
-                const float4* b4 = reinterpret_cast<const float4*>(btab_s + col0);
+            if constexpr (MODE == kF2Sdf) {
+              if (st.epi == EP_SOFTPLUS) {
+                float o[16];
+                if (col0 + 16 <= st.n_valid) {
+                  const float4* b4 = reinterpret_cast<const float4*>(btab_s + col0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 b = b4[i];
-                  o[4 * i + 0] = softplus_t(fmaf(acc[4 * i + 0], kSpK1, b.x), csp);
-                  o[4 * i + 1] = softplus_t(fmaf(acc[4 * i + 1], kSpK1, b.y), csp);
-                  o[4 * i + 2] = softplus_t(fmaf(acc[4 * i + 2], kSpK1, b.z), csp);
-                  o[4 * i + 3] = softplus_t(fmaf(acc[4 * i + 3], kSpK1, b.w), csp);
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 b = b4[i];
+                    o[4 * i + 0] = softplus_t(fmaf(acc[4 * i + 0], kSpK1, b.x), csp);
+                    o[4 * i + 1] = softplus_t(fmaf(acc[4 * i + 1], kSpK1, b.y), csp);
+                    o[4 * i + 2] = softplus_t(fmaf(acc[4 * i + 2], kSpK1, b.z), csp);
+                    o[4 * i + 3] = softplus_t(fmaf(acc[4 * i + 3], kSpK1, b.w), csp);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int n = col0 + i;
+                    float v = 0.f;
+                    if (n < st.n_valid) v = softplus_t(fmaf(acc[i], kSpK1, btab_s[n & 255]), csp);
+                    else if ((st.flags & TC_PEFILL) && n - st.n_valid < pe_w) v = pe_eval(xv[T], petab[n - st.n_valid]) * st.scale;
+                    o[i] = v;
+                  }
                 }
-              } else {
+                st_row16(A + (pc >> 2) * kBlk, m, pc & 3, o);
+              } else if (st.epi == EP_SDF) {
+                if (col0 == 0 && live[T]) {
+                  float y0 = acc[0] + btab_s[0];
+                  if (ch.radius > 0.f && p < ch.n_clamped) {
+                    // coordinates beyond d_in are zero
+                    const float n2 = xv[T][0] * xv[T][0] + xv[T][1] * xv[T][1] + xv[T][2] * xv[T][2] + xv[T][3] * xv[T][3];
+                    y0 = fminf(y0, ch.sph_scale * (ch.radius - sqrtf(n2)));
+                  }
+                  ch.sdf[p] = y0;
+                }
+              } else {   // EP_Y
+                if (st.n_valid == 1) {
+                  if (col0 == 0 && live[T]) ch.y[p * ch.ldy + st.y_col] = acc[0] + btab_s[0];
+                } else if (!last) {   // a later step still multiplies A_T: no scratch, direct (uncoalesced) stores
+                  if (live[T]) {
+                    float* dst = ch.y + p * ch.ldy + st.y_col + col0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int n = col0 + i;
-                  float v = 0.f;
-                  if (n < st.n_valid) v = softplus_t(fmaf(acc[i], kSpK1, btab_s[n & 255]), csp);
-                  else if ((st.flags & TC_PEFILL) && n - st.n_valid < pe_w) v = pe_eval(xv[T], petab[n - st.n_valid]) * st.scale;
-                  o[i] = v;
+                    for (int i = 0; i < 16; ++i)
+                      if (col0 + i < st.n_valid) dst[i] = acc[i] + btab_s[(col0 + i) & 255];
+                  }
+                } else {
+                  // y is fp32 row-major with a thread-per-row register layout: a direct store touches 32 lines per
+                  // instruction.  Transpose the 32 x 16 piece through this warp's scratch (inside the now free A_T) so
+                  // that every store instruction writes two rows x 16 contiguous floats.
+                  float* scr = reinterpret_cast<float*>(A) + ew * (32 * 17);
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) scr[lane * 17 + i] = acc[i] + btab_s[(col0 + i) & 255];
+                  __syncwarp();
+                  const int cc = lane & 15, n = col0 + cc;
+                  const int64_t row0 = pt[T] - lane;   // first row of this warp's lane quarter
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) {
+                    const int rr_ = 2 * k + (lane >> 4);
+                    const int64_t pr = row0 + rr_;
+                    if (pr < ch.P && n < st.n_valid) ch.y[pr * ch.ldy + st.y_col + n] = scr[rr_ * 17 + cc];
+                  }
+                  __syncwarp();
                 }
               }
-              st_row16(A + (pc >> 2) * kBlk, m, pc & 3, o);
-            } else if (st.epi == EP_SDF) {
-              if (col0 == 0 && live[T]) {
-                float y0 = acc[0] + btab_s[0];
-                if (ch.radius > 0.f && p < ch.n_clamped) {
-                  // coordinates beyond d_in are zero
-                  const float n2 = xv[T][0] * xv[T][0] + xv[T][1] * xv[T][1] + xv[T][2] * xv[T][2] + xv[T][3] * xv[T][3];
-                  y0 = fminf(y0, ch.sph_scale * (ch.radius - sqrtf(n2)));
-                }
-                ch.sdf[p] = y0;
-              }
-            } else {   // EP_Y
-              if (live[T]) {
-                float* dst = ch.y + p * ch.ldy + st.y_col + col0;
+            } else {
+              if (st.epi == EP_RELU) {
+                float o[16];
+                if (col0 + 16 <= st.n_valid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (col0 + i < st.n_valid) dst[i] = acc[i] + btab_s[(col0 + i) & 255];
+                  for (int i = 0; i < 16; ++i) o[i] = fmaxf(acc[i] + __ldg(st.bias + col0 + i), 0.f);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) o[i] = (col0 + i < st.n_valid) ? fmaxf(acc[i] + __ldg(st.bias + col0 + i), 0.f) : 0.f;
+                }
+                st_row16(A + (pc >> 2) * kBlk, m, pc & 3, o);
+              } else {   // EP_RGB
+                if (live[T]) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int n = col0 + i;
+                    if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + __expf(-(acc[i] + __ldg(st.bias + n))));
+                  }
+                }
               }
             }
           }
@@ -338,9 +462,13 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->a_full[T]);
           }
+          if (writes_a && all_save) pend |= 1u << T;
         }
       }
       tc_fence_before();
+      // the y stores of the last step use A_T as scratch: every warp must be done with it before any warp starts the
+      // next round's prologue
+      if (MODE == kF2Sdf && ch.st[ch.n_steps - 1].epi == EP_Y) named_bar_sync(1, kF2NW * 32);
     }
   }
   tc_fence_before();
@@ -348,14 +476,18 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-static int launch_fwd2(const TcChain& ch, int grid, cudaStream_t st) {
+template <int MODE>
+static int launch_fwd2_t(const TcChain& ch, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes));
+    SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F2Cfg<MODE>::kSmemBytes));
     attr_set = true;
   }
-  tc_fwd2_kernel<<<grid, kF2Threads, kF2SmemBytes, st>>>(ch);
+  tc_fwd2_kernel<MODE><<<grid, kF2Threads, F2Cfg<MODE>::kSmemBytes, st>>>(ch);
   return SVS_OK;
+}
+static int launch_fwd2(const TcChain& ch, int grid, cudaStream_t st) {
+  return ch.prologue == PRO_RENDER_IN ? launch_fwd2_t<kF2Render>(ch, grid, st) : launch_fwd2_t<kF2Sdf>(ch, grid, st);
 }
 
 }  // namespace tc

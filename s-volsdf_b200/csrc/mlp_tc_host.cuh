@@ -314,7 +314,12 @@ static int launch_chain(TcChain& ch, const char* name, double flops, double byte
       SVS_TRY((launch_chain_t<kEpiFwd, PRO_PE, kNwFwd>(ch, grid, st)));
       break;
     case PRO_LOAD_ULAST: SVS_TRY((launch_chain_t<kEpiRev, PRO_LOAD_ULAST, kNwRev>(ch, grid, st))); break;
-    case PRO_RENDER_IN: SVS_TRY((launch_chain_t<kEpiRenderFwd, PRO_RENDER_IN, kNwRenderFwd>(ch, grid, st))); break;
+    case PRO_RENDER_IN:
+#ifndef SVS_TC_NO_FWD2
+      if (fwd2_supports(ch)) { SVS_TRY(launch_fwd2(ch, grid, st)); break; }
+#endif
+      SVS_TRY((launch_chain_t<kEpiRenderFwd, PRO_RENDER_IN, kNwRenderFwd>(ch, grid, st)));
+      break;
     case PRO_SIGMOID_BWD: SVS_TRY((launch_chain_t<kEpiRenderBwd, PRO_SIGMOID_BWD, kNwRenderBwd>(ch, grid, st))); break;
     case PRO_PE_JVP: SVS_TRY((launch_chain_t<kEpiTan, PRO_PE_JVP, kNwTan>(ch, grid, st))); break;
     case PRO_DY: SVS_TRY((launch_chain_t<kEpiBwd, PRO_DY, kNwBwd>(ch, grid, st))); break;
