@@ -72,9 +72,10 @@ __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min
   return fabsf(__ldg(beta_param)) + beta_min;  // density.py:28-30
 }
 
-// FAST (SVS_COMP_FAST, opt-in; the models do not set it): MUFU exp and fp32 scans instead of the canonical arithmetic
-// (libm expf, fp64 prefix sums) that reproduces the oracle; |weights| differ by ~1e-6.  Measured gain at 262144 rays:
-// 5-8 % — the kernels are bound by per-ray instruction count, not by the transcendentals.
+// FAST (SVS_COMP_FAST; set by the models when the tcgen05 engine is selected, whose fp16 MLP error is 1e-3): MUFU
+// exp, fp32 scans and reciprocal multiplies instead of the canonical arithmetic (libm expf / expm1f, fp64 prefix sums,
+// IEEE divisions) that reproduces the oracle; weights differ by ~1e-6.  The exact path costs ~1400 instructions per
+// ray and lane, which bounds it far below the HBM roofline; FAST is the bandwidth-bound variant.
 template <bool FAST>
 __device__ __forceinline__ float exp_t(float x) { return FAST ? __expf(x) : expf(x); }
 
@@ -85,11 +86,18 @@ __device__ __forceinline__ float density_fwd(float s, float beta, bool abs_densi
     *em_out = 0.f;
     return fabsf(s);
   }
-  // expm1f stays the libm one even in FAST mode: with the reference's last interval of 1e10 (network.py:286) the
-  // rounding of em and em + 1 is amplified by 1e10 in d beta, and parity means reproducing exactly that rounding
+  float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  if (FAST) {
+    // em = fl(e^-x - 1): for e^-x < 1/8 the MUFU error is below half the rounding quantum of (e - 1), so em lands on
+    // the same fp32 value as expm1f -- which matters because the reference's last interval of 1e10 (network.py:286)
+    // amplifies the rounding of em + 1 (sigma is exactly 0 once e^-x < 3e-8, as in the reference)
+    const float ib = __frcp_rn(beta);
+    const float em = __expf(-fabsf(s) * ib) - 1.0f;
+    *em_out = em;
+    return ib * (0.5f + 0.5f * sg * em);
+  }
   float em = expm1f(-fabsf(s) / beta);
   *em_out = em;
-  float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
   return (1.0f / beta) * (0.5f + 0.5f * sg * em);
 }
 
@@ -114,6 +122,29 @@ __device__ __forceinline__ T warp_excl_scan(const float (&v)[C], T (&excl)[C], i
 #pragma unroll
   for (int j = 0; j < C; ++j) excl[j] += base;
   return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// suffix sums suf[j] = sum of the elements AFTER element (lane, j) in the lane-contiguous order: a reverse scan, so
+// the last element's suffix is exactly 0 and nothing cancels (a `total - prefix` in fp32 leaves a 1e-7 residue that
+// the reference's last interval of 1e10 would blow up in d sigma)
+template <int C>
+__device__ __forceinline__ void warp_suffix_scan(const float (&v)[C], float (&suf)[C], int lane) {
+  float run = 0.f;
+#pragma unroll
+  for (int j = C - 1; j >= 0; --j) {
+    suf[j] = run;
+    run += v[j];
+  }
+  float incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  float base = __shfl_down_sync(0xffffffffu, incl, 1);   // total of the lanes after this one
+  if (lane == 31) base = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) suf[j] += base;
 }
 
 template <int C, bool FAST>
@@ -298,6 +329,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     __syncwarp();
     const CompRows<C>& in = sm.in[warp][k];
     const float gr = cq.gr, gg = cq.gg, gb = cq.gb, gdep = cq.gdep, gbt = cq.gbt, ds = cq.ds;
+    const float ib = __frcp_rn(beta), i2b2 = __frcp_rn(2.0f * beta * beta);
     using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C], dl[C], sig[C], em[C], ss[C];
     ScanT excl[C];
@@ -336,6 +368,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     acc_w = warp_sum(acc_w);
     acc_wz = warp_sum(acc_wz);
     const float Wt = acc_w + 1e-8f;
+    const float iWt2 = __frcp_rn(Wt * Wt);
     // w_hat_i = c_i . dL/drgb + dL/dw_i + dL/ddepth * ds * (z_i*Wt - sum(wz)) / Wt^2
     float what[C], ww[C];
 #pragma unroll
@@ -345,21 +378,24 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       if (i < S) {
         if (rgb) v = in.c[3 * i] * gr + in.c[3 * i + 1] * gg + in.c[3 * i + 2] * gb;
         if (d_weights) v += in.g[i];
-        v += gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
+        v += FAST ? gdep * ds * (zz[j] * Wt - acc_wz) * iWt2 : gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
       }
       what[j] = v;
       ww[j] = v * w[j];
     }
     // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
     ScanT excl2[C];
-    ScanT tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);
+    ScanT tot2 = 0;
+    float suf[C];
+    if (FAST) warp_suffix_scan<C>(ww, suf, lane);
+    else tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);
     const float bgt = tail ? exp_t<FAST>(-(float)total) : 0.f;
     float dbeta = 0.f;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       if (i < S) {
-        float suffix = (float)(tot2 - excl2[j] - (ScanT)ww[j]);
+        float suffix = FAST ? suf[j] : (float)(tot2 - excl2[j] - (ScanT)ww[j]);
         float dE = what[j] * Te[j] - suffix - gbt * bgt;
         float dsig = dl[j] * dE;
         float dsdf;
@@ -369,8 +405,13 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
         } else {
           float e = em[j] + 1.0f;  // autograd's expm1 backward uses result + 1
           float nz = (ss[j] != 0.f) ? 1.f : 0.f;
-          dsdf = -dsig * nz * e / (2.0f * beta * beta);
-          dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
+          if (FAST) {
+            dsdf = -dsig * nz * e * i2b2;
+            dbeta += dsig * (-sig[j] * ib + ss[j] * e * (i2b2 * ib));
+          } else {
+            dsdf = -dsig * nz * e / (2.0f * beta * beta);
+            dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
+          }
         }
         sm.o[warp][i] = dsdf;   // rows leave through shared memory: coalesced stores
         sm.w[warp][i] = w[j];

@@ -196,6 +196,11 @@ class VolSDFNetwork(nn.Module):
         self.rendering_network.engine = engine
         return self
 
+    def _comp_flags(self):
+        """The tcgen05 engine (fp16 MLP operands, 1e-3) composites with the bandwidth-bound arithmetic (MUFU exp, fp32
+        scans: weights within 1e-6 of the canonical one); the fp32 parity engine keeps the canonical arithmetic."""
+        return L.COMP_FAST if self.implicit_network.engine == L.ENGINE_TC else 0
+
     def _rays(self, uv, pose, intrinsics):
         dirs, cams, scales = [], [], []
         for b in range(uv.shape[0]):
@@ -244,7 +249,7 @@ class VolSDFNetwork(nn.Module):
         rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, y, _feat_col=1)
         weights, rgb_values, depth_values, normal_map, _ = F.composite(
             z_vals, sdf, rgb_flat, self.density.beta, float(self.density.beta_min), depth_scale,
-            normals=None if self.training else gradients)
+            normals=None if self.training else gradients, flags=self._comp_flags())
 
         if self.white_bkgd:
             acc_map = torch.sum(weights, -1)

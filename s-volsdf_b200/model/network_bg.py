@@ -38,6 +38,10 @@ class VolSDFNetworkBG(nn.Module):
             m.engine = engine
         return self
 
+    def _comp_flags(self):
+        """see VolSDFNetwork._comp_flags: bandwidth-bound compositing arithmetic with the tcgen05 engine"""
+        return L.COMP_FAST if self.implicit_network.engine == L.ENGINE_TC else 0
+
     def forward(self, input, fast=-1):
         if not self.training:
             with torch.no_grad():
@@ -67,7 +71,7 @@ class VolSDFNetworkBG(nn.Module):
         rgb_flat = self.rendering_network(points_flat, gradients, dirs_flat, y, _feat_col=1)
         weights, fg_rgb_values, depth_values, normal_map, bg_transmittance = F.composite(
             z_vals, sdf, rgb_flat, self.density.beta, float(self.density.beta_min), depth_scale,
-            normals=None if self.training else gradients, z_max=z_max, flags=L.COMP_ZMAX_TAIL)
+            normals=None if self.training else gradients, z_max=z_max, flags=L.COMP_ZMAX_TAIL | self._comp_flags())
 
         # background: inverted-sphere samples 1 -> 0 (network_bg.py:82-101)
         Sb = z_vals_bg.shape[1]
@@ -82,7 +86,7 @@ class VolSDFNetworkBG(nn.Module):
         bg_rgb_flat = self.bg_rendering_network(None, None, bg_dirs_flat, yb, _feat_col=1)
         bg_weights, bg_rgb_values, _, _, _ = F.composite(
             z_bg, yb[:, 0].reshape(R, Sb), bg_rgb_flat, None, 0.0, None,
-            flags=L.COMP_ABS_DENSITY | L.COMP_REVERSED)
+            flags=L.COMP_ABS_DENSITY | L.COMP_REVERSED | self._comp_flags())
 
         # blend (network_bg.py:103-114)
         weights_all = torch.cat([weights, bg_transmittance[:, None] * bg_weights], 1)
