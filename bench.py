@@ -360,7 +360,7 @@ def run_ours(args):
     L.prof_enable(False)
     model.rng_source = None
     pk = peaks()
-    roofline, kernels = None, {}
+    roofline, rooflines, kernels = None, [], {}
     traffic_tab = {}
     tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tp):
@@ -370,17 +370,29 @@ def run_ours(args):
         for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             kernels[name] = {'launches_per_step': v['launches'] / n_prof, 'ms_per_step': v['ms'] / n_prof,
                              'share_of_kernel_time': v['ms'] / tot_ms}
+        def entry(name, v):
+            """both rooflines of one kernel; `bound` = the one it sits closer to.  achieved = ALGORITHMIC flops / bytes
+            (SURVEY.md 8d figures, passed by the library with every launch) over the CUDA-event time."""
+            sec = v['ms'] * 1e-3
+            tf = v['flops'] / sec / 1e12 if v['flops'] > 0 else 0.0
+            gb = v['bytes'] / sec / 1e9 if v['bytes'] > 0 else 0.0
+            f_t, f_h = tf / pk['tflops_sustained'], gb / pk['hbm_gbs']
+            tr = traffic_tab.get(name)
+            e = {'kernel': name, 'avg_launch_ms': v['ms'] / v['launches'], 'traffic': tr,
+                 'tensor_frac': f_t, 'hbm_frac': f_h if gb > 0 else None,
+                 # measured DRAM bytes (ncu, per launch) over the live launch time: how close the kernel is to the HBM
+                 # roofline counting everything it actually moves (saved activation tiles included)
+                 'hbm_frac_measured_traffic': (tr / (v['ms'] / v['launches'] * 1e-3) / 1e9 / pk['hbm_gbs']) if tr else None}
+            if f_h > f_t:
+                e.update({'bound': 'hbm', 'achieved': gb, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': f_h,
+                          'peak_source': pk['source']})
+            else:
+                e.update({'bound': 'tensor', 'achieved': tf, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                          'frac': f_t, 'peak_source': pk['source'] + ' bf16 sustained'})
+            return e
         name, v = max(prof.items(), key=lambda kv: kv[1]['ms'])
-        if v['flops'] > 0:
-            ach = v['flops'] / (v['ms'] * 1e-3) / 1e12
-            roofline = {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk['tflops_sustained'],
-                        'unit': 'TFLOP/s', 'frac': ach / pk['tflops_sustained'], 'traffic': traffic_tab.get(name),
-                        'avg_launch_ms': v['ms'] / v['launches'], 'peak_source': pk['source'] + ' bf16 sustained'}
-        else:
-            ach = v['bytes'] / (v['ms'] * 1e-3) / 1e9
-            roofline = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                        'frac': ach / pk['hbm_gbs'], 'traffic': traffic_tab.get(name), 'avg_launch_ms': v['ms'] / v['launches'],
-                        'peak_source': pk['source']}
+        roofline = entry(name, v)
+        rooflines = [entry(n_, v_) for n_, v_ in sorted(prof.items(), key=lambda kv: -kv[1]['ms']) if v_['flops'] > 0 or v_['bytes'] > 0]
 
     # ---- the fp32 parity engine on the same step, for reference (not the headline) ----
     parity = None
@@ -399,9 +411,22 @@ def run_ours(args):
         model.set_engine(engine)
     model.rng_source = None
 
+    def leave():
+        """End of a multi-rank run.  destroy_process_group() was seen to block forever once the communicator has been
+        used inside a captured CUDA graph (2-GPU run: the JSON line was out, both ranks sat in the destructor until the
+        launcher's timeout): drop the graph, drain the device, meet once more, then leave without the destructor."""
+        nonlocal graphed
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            leave()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -422,11 +447,11 @@ def run_ours(args):
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         'algorithmic_tflops': step_tflops, 'algorithmic_frac_of_tensor_peak': step_tflops * 1.0 / world / pk['tflops_sustained'],
-        'kernels': kernels, 'parity_engine': parity,
+        'kernels': kernels, 'rooflines': rooflines, 'parity_engine': parity,
     }
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        leave()
 
 
 F_SDF, F_RENDER = 1049088.0, 533504.0   # FLOP per point-forward, SURVEY.md Appendix B

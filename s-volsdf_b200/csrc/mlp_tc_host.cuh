@@ -301,10 +301,12 @@ static int launch_chain_t(const TcChain& ch, int grid, cudaStream_t st) {
 constexpr int kNwFwd = SVS_TC_NW_FWD, kNwRev = SVS_TC_NW_REV, kNwRenderFwd = SVS_TC_NW_RFWD, kNwRenderBwd = SVS_TC_NW_RBWD,
               kNwTan = SVS_TC_NW_TAN, kNwBwd = SVS_TC_NW_BWD;
 
+static double chain_bytes(const TcChain& ch);
 static int launch_chain(TcChain& ch, const char* name, double flops, double bytes, cudaStream_t st) {
   ch.n_tiles = (int)n_tiles_of(ch.P);
   if (ch.n_tiles <= 0) return SVS_OK;
   const int grid = ch.n_tiles < num_sms() ? ch.n_tiles : num_sms();
+  if (bytes <= 0.0) bytes = chain_bytes(ch);
   ProfScope ps(name, flops, bytes, st);
   switch (ch.prologue) {
     case PRO_PE:
@@ -348,6 +350,30 @@ static double chain_flops(const TcChain& ch) {
   return f * (double)ch.P;
 }
 
+// bytes a chain has to move by construction: the fp16 tile images it loads / saves (activations kept for the backward
+// and the weight gradients) and its fp32 row-major inputs / outputs; weights are L2-resident and not counted
+static double chain_bytes(const TcChain& ch) {
+  double per_tile = 0, per_point = 0;
+  if (ch.pro_save >= 0) per_tile += (double)ch.pro_kb * kBlk;
+  if (ch.prologue == PRO_LOAD_ULAST) per_tile += (double)ch.pro_kb * kBlk;
+  for (int s = 0; s < ch.n_steps; ++s) {
+    const TcStep& st = ch.st[s];
+    const int nchunk = (st.n_pad + 63) >> 6;
+    per_tile += (double)((st.aux1 >= 0) + (st.aux2 >= 0) + (st.epi == EP_TANGENT)) * nchunk * kBlk;
+    if (st.save >= 0) per_tile += (double)st.next_kb * kBlk;
+    if (st.epi == EP_Y || st.epi == EP_DFEAT) per_point += 4.0 * st.n_valid;
+    if (st.epi == EP_SDF || st.epi == EP_PEGRAD) per_point += 4.0 * (1 + (ch.grad ? ch.d_in : 0));
+    if (st.epi == EP_RGB) per_point += 4.0 * st.n_valid;
+    if (st.epi == EP_DSMALL) per_point += 12.0;
+  }
+  if (ch.x) per_point += 4.0 * ch.d_in;
+  if (ch.prologue == PRO_RENDER_IN) per_point += 4.0 * ch.F + 36.0;
+  if (ch.prologue == PRO_SIGMOID_BWD) per_point += 8.0 * ch.n_rgb;
+  if (ch.prologue == PRO_PE_JVP) per_point += 4.0 * ch.d_in;
+  if (ch.prologue == PRO_DY) per_point += 4.0 * ch.dy_cols + 4.0;
+  return per_tile * (double)n_tiles_of(ch.P) + per_point * (double)ch.P;
+}
+
 // split the CTAs of one weight-gradient launch over the jobs in proportion to their MMA work
 static int launch_dw(DwParams& prm, int64_t P, cudaStream_t st) {
   static bool attr_set = false;
@@ -365,7 +391,7 @@ static int launch_dw(DwParams& prm, int64_t P, cudaStream_t st) {
   }
   const int budget = num_sms();   // one wave: every CTA streams its share of the tiles once and reduces once
   int unit = 0;
-  double flops = 0;
+  double flops = 0, bytes = 0;
   for (int j = 0; j < prm.n_jobs; ++j) {
     DwJob& jb = prm.job[j];
     int n = (int)(budget * cost[j] / total);   // floor: the total never exceeds one wave
@@ -375,8 +401,13 @@ static int launch_dw(DwParams& prm, int64_t P, cudaStream_t st) {
     jb.n_split = n;
     unit += n;
     flops += 2.0 * (double)P * jb.n_pairs * jb.n_rows * jb.n_cols;
+    // operand bytes the job has to stream: every tile's X and Y blocks, once per pair
+    int nxb = 0;
+    for (int b = 0; b < 2 * jb.n_mblk; ++b)
+      if (jb.x_blk0 + b < jb.x_kb) ++nxb;
+    bytes += (double)prm.n_tiles * jb.n_pairs * (nxb + jb.n_yblk) * kBlk;
   }
-  ProfScope ps("mlp_tc_dw", flops, 0.0, st);
+  ProfScope ps("mlp_tc_dw", flops, bytes, st);
   tc_dw_kernel<<<unit, 192, kDwSmem, st>>>(prm);
   SVS_LAUNCH_OK();
   return SVS_OK;
