@@ -114,8 +114,8 @@ class ClockSampler(object):
 def cpu_train_steps(n_rays, steps, warmup, threads=None):
     import svolsdf_b200.conf as C
     import svolsdf_b200.scene as S
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 for every rank)
+    torch.set_num_threads(threads or max(1, min(os.cpu_count() or 1, 64)))
     kind = 'port'
     inp = S.make_input('dtu', n_rays)
     gt = S.gt_rgb(n_rays)

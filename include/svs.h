@@ -26,7 +26,7 @@ extern "C" {
 
 #define SVS_MAX_LAYERS 12
 #define SVS_OPT_MAX_TENSORS 96
-#define SVS_ABI_VERSION 3
+#define SVS_ABI_VERSION 4
 
 typedef enum {
   SVS_OK = 0,
@@ -244,6 +244,29 @@ int svs_density_backward(const float* sdf, int64_t R, int32_t S, const float* be
 int svs_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
                   float max_norm, int32_t skip_nonfinite, const float* step_count, float* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MVS cost lookup of the reference's training loop — VolOpt.cost_mapping (volsdf/vsdf.py:382-452).
+ * Every ray sample xyz (N, D, 3) is projected into each source view (pose, pinhole with skew, normalised at image
+ * resolution img_h x img_w), the view's per-pixel depth range is read with two bilinear lookups, the probability
+ * volume with one trilinear lookup (grid_sample: bilinear, zero padding, align_corners=True).  Outputs, all (N, D):
+ *   cost_j   sum over the views with same_view == 0                       (results_cost_j, the loss's `pj`)
+ *   cost_mvs the view with same_view == 1, zeroed where valid == 0        (results_cost_mvs, the loss's `pi`)
+ *   valid    1 where the sample lies inside the frustum and depth range of at least one other view (valid_mask)
+ * `views` is a HOST array of n_views (<= 8) descriptors holding DEVICE pointers; nothing is retained after the call.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct svs_mvs_view {
+  const float* cost;   /* (Dz, H, W) probability volume            (self.costs[i][0],  vsdf.py:369) */
+  const float* z_near; /* (H, W) first depth hypothesis plane       (self.z_mvs[i][0, 0],  vsdf.py:420) */
+  const float* z_far;  /* (H, W) last depth hypothesis plane        (self.z_mvs[i][0, -1]) */
+  int32_t Dz, H, W;
+  float fx, fy, cx, cy, sk; /* K[0,0], K[1,1], K[0,2], K[1,2], K[0,1] of the view (vsdf.py:398-399) */
+  float c2w[12];            /* rows 0..2 of the camera-to-world pose, row-major (vsdf.py:396-397) */
+  int32_t same_view;        /* 1: the batch's own image (ts[0] == id_k, vsdf.py:392) */
+} svs_mvs_view;
+int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views,
+                     int32_t img_h, int32_t img_w, int32_t inverse_depth, float* cost_j, float* cost_mvs,
+                     uint8_t* valid, void* stream);
 
 #ifdef __cplusplus
 }

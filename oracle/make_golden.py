@@ -199,6 +199,72 @@ def unit_vectors(ns):
     print('%-28s %8.1f KB' % ('units', os.path.getsize(path) / 1024.0))
 
 
+def reference_cost_mapping():
+    """VolOpt.cost_mapping as the reference wrote it: volsdf/vsdf.py cannot be imported here (pyhocon, tensorboard and
+    a dataset on disk), so the method's source is cut out of the file with `ast` at run time and compiled on its own —
+    executed verbatim, never copied into this repo."""
+    import ast
+    path = os.path.join(ref_import.REF_ROOT, 'volsdf', 'vsdf.py')
+    tree = ast.parse(open(path).read())
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == 'cost_mapping':
+            fn = node
+    assert fn is not None
+    fn.decorator_list = []
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    scope = {'torch': torch, 'grid_sample': torch.nn.functional.grid_sample}
+    exec(compile(mod, path, 'exec'), scope)
+    return scope['cost_mapping']
+
+
+def mvs_case(ns):
+    """cost_mapping + VolSDFLoss with the MVS terms on, on the synthetic MVS scene of svolsdf_b200.scene.mvs_views."""
+    import types
+    import svolsdf_b200.scene as S
+    img_res = (72, 96)
+    views = S.mvs_views(img_res=img_res)
+    xyz = S.mvs_points()
+    ids = [25, 22, 28]
+    fake = types.SimpleNamespace(
+        trains_i=ids, costs={i: v['cost'][None] for i, v in enumerate(views)},
+        z_mvs={i: v['z_mvs'][None] for i, v in enumerate(views)},
+        train_dataset=types.SimpleNamespace(img_res=list(img_res), intrinsics_all={k: views[i]['K'] for i, k in enumerate(ids)},
+                                            pose_all={k: views[i]['c2w'] for i, k in enumerate(ids)}),
+        hparams=types.SimpleNamespace(inverse_depth=True), stg=0)
+    fn = reference_cost_mapping()
+    # the volumes are not stored: the test side re-creates them from the seed; a checksum guards that
+    out = {'xyz': xyz.numpy(), 'views_checksum': np.asarray(sum(float(v[k].double().sum()) for v in views for k in ('cost', 'z_mvs', 'K', 'c2w')))}
+    for tag, same, inv in (('own1_inv', 22, True), ('none_inv', 99, True), ('own0_lin', 25, False)):
+        fake.hparams.inverse_depth = inv
+        with torch.no_grad():
+            cj, cm, va = fn(fake, torch.zeros(xyz.shape[:2]), torch.tensor([same]), xyz.clone())
+        out[tag + '_cost_j'], out[tag + '_cost_mvs'], out[tag + '_valid'] = cj.numpy(), cm.numpy().copy(), va.numpy()
+    # the loss with its MVS / sparsity terms (loss.py:80-115), three generalised-cross-entropy settings
+    if ns.loss is not None:
+        g = torch.Generator().manual_seed(8)
+        N, D = xyz.shape[:2]
+        mo = {'rgb_values': torch.rand(N, 3, generator=g), 'grad_theta': torch.randn(2 * N, 3, generator=g),
+              'weights': torch.softmax(torch.randn(N, D, generator=g), -1) * 0.9, 'depth_values': torch.rand(N, 1, generator=g) + 1.5,
+              'pj': torch.from_numpy(out['own1_inv_cost_j']), 'pi': torch.from_numpy(out['own1_inv_cost_mvs'])}
+        gt = {'rgb': torch.rand(1, N, 3, generator=g), 'rgb_smooth': None}
+        gt['rgb_smooth'] = gt['rgb']
+        for k in ('rgb_values', 'grad_theta', 'weights', 'depth_values'):
+            out['loss_in_' + k] = mo[k].numpy()
+        out['loss_in_rgb'] = gt['rgb'].numpy()
+        for gce in (1, 0, 0.5):
+            for sparse in (0.0, 0.3):
+                L_ = ns.loss.VolSDFLoss('torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=0.5, sparse_weight=sparse, anneal_rgb=100 if sparse else 0,
+                                        gce=gce, confi=0.02)
+                L_.iter_step = 25
+                r = L_(mo, gt)
+                for k, v_ in r.items():
+                    out['loss_gce%s_sp%s_%s' % (gce, sparse, k)] = np.asarray(float(v_))
+    np.savez_compressed(os.path.join(OUT, 'mvs_cost_mapping.npz'), **out)
+    print('mvs_cost_mapping.npz', {k: (v.shape if hasattr(v, 'shape') else v) for k, v in out.items() if 'loss_gce' in k or 'valid' in k})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_import.load()
@@ -210,6 +276,7 @@ def main():
     run_case(ns, 'dtu_train_r64_pert', 'dtu', 64, True, perturb=True, beta=0.02)
     run_case(ns, 'bmvs_eval_r32', 'bmvs', 32, False, perturb=True, beta=0.02)
     run_case(ns, 'bmvs_train_r32', 'bmvs', 32, True, perturb=True)
+    mvs_case(ns)
 
 
 if __name__ == '__main__':

@@ -564,6 +564,105 @@ def volsdf_loss(out, rgb_gt, eikonal_weight=0.1):
 
 
 # --------------------------------------------------------------------------------------------
+# MVS cost lookup + full loss of the training loop        volsdf/vsdf.py:382-452, volsdf/model/loss.py:80-115
+# --------------------------------------------------------------------------------------------
+
+
+def _lerp_lookup(vol, coords):
+    """grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) of ONE channel, spelled out.
+    vol: (H, W) with coords (..., 2) = (x, y), or (Dz, H, W) with coords (..., 3) = (x, y, z); coords in [-1, 1]."""
+    dims = list(vol.shape)[::-1]                       # sizes along x, y(, z)
+    pos = [(coords[..., k] + 1.0) / 2.0 * (dims[k] - 1) for k in range(len(dims))]
+    lo = [torch.floor(p_) for p_ in pos]
+    out = torch.zeros_like(pos[0])
+    for corner in range(1 << len(dims)):
+        w = torch.ones_like(pos[0])
+        idx, ok = [], torch.ones_like(pos[0], dtype=torch.bool)
+        for k in range(len(dims)):
+            hi = (corner >> k) & 1
+            c = lo[k] + hi
+            w = w * ((pos[k] - lo[k]) if hi else (lo[k] + 1.0 - pos[k]))
+            ok = ok & (c >= 0) & (c <= dims[k] - 1)
+            idx.append(c.clamp(0, dims[k] - 1).long())
+        val = vol[idx[1], idx[0]] if len(dims) == 2 else vol[idx[2], idx[1], idx[0]]
+        out = out + torch.where(ok, w * val, torch.zeros_like(w))
+    return out
+
+
+def cost_mapping(xyz, views, img_res, same_view_index, inverse_depth=True):
+    """VolOpt.cost_mapping (vsdf.py:382-452).  xyz (N, D, 3) world points; views: list of dicts with cost (Dz,H,W),
+    z_mvs (Dz,H,W), K (4,4), c2w (4,4); same_view_index: position in `views` of the batch's own image or -1.
+    Returns results_cost_j (N,D), results_cost_mvs (N,D), valid_mask (N,D) bool."""
+    h, w = img_res
+    N, D, _ = xyz.shape
+    cost_sum = torch.zeros(N, D, dtype=xyz.dtype)
+    cost_own = torch.zeros(N, D, dtype=xyz.dtype)
+    valid = torch.zeros(N, D, dtype=torch.bool)
+    for i, v in enumerate(views):
+        K, c2w = v['K'], v['c2w'][:3]
+        fx, fy, cx, cy, sk = K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1]          # :395-399
+        p = (xyz - c2w[:, 3].view(1, 1, 3)) @ c2w[:, :3]                           # :401-402 world -> camera
+        z = p[..., 2]
+        x, y = p[..., 0] / z, p[..., 1] / z                                        # :406
+        y = y * fy + cy                                                            # :407
+        x = x * fx + cx + (y - cy) * sk / fy                                       # :408
+        x = x / ((w - 1) / 2) - 1                                                  # :410-411
+        y = y / ((h - 1) / 2) - 1
+        bad = (z < 1e-5) | (x > 1.001) | (x < -1.001) | (y > 1.001) | (y < -1.001)  # :418
+        x, y, z = [torch.where(bad, torch.full_like(t, -99.0), t) for t in (x, y, z)]   # :419
+        xy = torch.stack([x, y], -1)
+        near = _lerp_lookup(v['z_mvs'][0], xy)                                     # :420,424
+        far = _lerp_lookup(v['z_mvs'][-1], xy)                                     # :425
+        if inverse_depth:                                                          # :426-428
+            far = torch.where(bad, torch.full_like(far, 1e-8), far)
+            zn = 2 * (1.0 - near / z) / (1.0 - near / far) - 1
+        else:                                                                      # :432
+            zn = 2 * (z - near) / (far - near) - 1
+        bad2 = (near < 1e-5) | (far < 1e-5) | (zn > 1.01) | (zn < -1.01) | bad      # :434
+        x, y, zn = [torch.where(bad2, torch.full_like(t, -99.0), t) for t in (x, y, zn)]   # :435
+        c = _lerp_lookup(v['cost'], torch.stack([x, y, zn], -1))                   # :440
+        if i == same_view_index:                                                   # :443-444
+            cost_own = c
+        else:                                                                      # :446-448
+            cost_sum = cost_sum + c
+            valid = valid | ~bad2
+    cost_own = torch.where(valid, cost_own, torch.zeros_like(cost_own))            # :450
+    return cost_sum, cost_own, valid
+
+
+def volsdf_full_loss(out, rgb_gt, eikonal_weight=0.1, rgb_weight=1.0, mvs_weight=0.0, sparse_weight=0.0, gce=1.0,
+                     confi=0.0, anneal_sparse=0.0):
+    """VolSDFLoss.forward (loss.py:80-115) with rgb_loss=L1Loss(mean); `out` may carry 'pi'/'pj' from cost_mapping.
+    anneal_sparse is the linear annealing factor of loss.py:101-104 (0 outside the annealing window: then the rgb term
+    is the plain L1 and the sparsity term is off)."""
+    dt = out['rgb_values'].dtype
+    res = {}
+    diff = (out['rgb_values'] - rgb_gt.reshape(-1, 3).to(dt)).abs()
+    res['rgb_loss'] = diff.mean()                                                  # :38-47
+    res['eikonal_loss'] = ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean() if 'grad_theta' in out else torch.zeros((), dtype=dt)
+    res['mvs_loss'] = torch.zeros((), dtype=dt)
+    res['sparse_loss'] = torch.zeros((), dtype=dt)
+    if 'pi' in out and mvs_weight > 0:                                             # :53-68
+        pw = out['pi'] * out['pj']
+        wgt = out['weights']
+        if gce == 1:
+            l = -pw * wgt
+        elif gce == 0:
+            l = -pw * torch.log(wgt + 1e-8)
+        else:
+            l = -pw * wgt.detach() ** gce * torch.log(wgt + 1e-8)
+        res['mvs_loss'] = ((pw.sum(1) > confi).to(dt) * l.sum(1)).mean()
+    if 'pi' in out and sparse_weight > 0 and anneal_sparse > 0:                    # :70-78, 96-104
+        conf_ray = (out['pi'] * out['pj']).sum(-1)
+        dep = (out['depth_values_all'] if 'depth_values_all' in out else out['depth_values']).squeeze()
+        res['sparse_loss'] = ((1.0 / (dep + 1e-3)) * (conf_ray < confi)).mean()
+        res['rgb_loss'] = (diff.mean(-1) * (conf_ray < 1e-8)).mean()               # :40-45 with t=1e-8 (rgb_smooth ground truth)
+    res['loss'] = rgb_weight * res['rgb_loss'] + eikonal_weight * res['eikonal_loss'] + mvs_weight * res['mvs_loss'] + \
+        sparse_weight * anneal_sparse * res['sparse_loss']                         # :107-110
+    return res
+
+
+# --------------------------------------------------------------------------------------------
 # BlendedMVS model forward                                volsdf/model/network_bg.py:37-145
 # --------------------------------------------------------------------------------------------
 

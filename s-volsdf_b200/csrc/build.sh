@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds libsvolsdf_b200.so in-tree for sm_100a.  sampler.cu / composite.cu / rays.cu use -fmad=false so
+# Builds libsvolsdf_b200.so in-tree for sm_100a.  sampler.cu / composite.cu / rays.cu / mvs.cu use -fmad=false so
 # the canonical fp32 arithmetic of the oracle (no fused multiply-add) is reproduced exactly.
 set -euo pipefail
 cd "$(dirname "$0")"
@@ -11,7 +11,7 @@ pids=()
 for f in capi mlp optim; do
   $NVCC $ARCH $COMMON -Xptxas -v -c $f.cu -o build/$f.o > build/$f.log 2>&1 & pids+=($!)
 done
-for f in sampler composite rays; do
+for f in sampler composite rays mvs; do
   $NVCC $ARCH $COMMON -fmad=false -Xptxas -v -c $f.cu -o build/$f.o > build/$f.log 2>&1 & pids+=($!)
 done
 fail=0

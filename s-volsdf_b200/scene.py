@@ -100,3 +100,41 @@ def perturb_(model, seed=7, w_std=PERTURB_W, b_std=PERTURB_B, beta=None):
             elif name == 'density.beta' and beta is not None:
                 p.fill_(beta)
     return model
+
+
+def mvs_views(n_views=3, dz=48, h=36, w=48, img_res=(72, 96), seed=5):
+    """Synthetic stand-in for the MVS stage-0 outputs VolOpt keeps per source view (volsdf/vsdf.py:364-379): a
+    probability volume (Dz, H, W), per-pixel depth hypotheses z_mvs (Dz, H, W, increasing along Dz), the view's
+    intrinsics at image resolution `img_res` = (height, width) and its camera-to-world pose.  Cameras sit on a circle
+    of radius 2.5 around the origin and look at it (the geometric-init sphere), a few degrees apart."""
+    g = torch.Generator().manual_seed(seed)
+    H, W = img_res
+    views = []
+    for i in range(n_views):
+        ang = (i - (n_views - 1) / 2.0) * 0.25
+        c = torch.tensor([2.5 * np.sin(ang), 0.15 * i, -2.5 * np.cos(ang)], dtype=torch.float32)
+        fwd = -c / c.norm()
+        right = torch.linalg.cross(torch.tensor([0.0, 1.0, 0.0]), fwd)
+        right = right / right.norm()
+        up = torch.linalg.cross(fwd, right)
+        c2w = torch.eye(4, dtype=torch.float32)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, up, fwd, c
+        K = torch.eye(4, dtype=torch.float32)
+        K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[0, 1] = 1.1 * W, 1.1 * W, W / 2.0 - 0.5, H / 2.0 - 0.5, 0.3
+        near = 1.4 + 0.2 * torch.rand(h, w, generator=g)
+        far = 3.4 + 0.3 * torch.rand(h, w, generator=g)
+        t = torch.linspace(0, 1, dz).view(dz, 1, 1)
+        z_mvs = near[None] * (1 - t) + far[None] * t
+        cost = torch.softmax(4.0 * torch.randn(dz, h, w, generator=g), 0)
+        views.append({'cost': cost.contiguous(), 'z_mvs': z_mvs.contiguous(), 'K': K, 'c2w': c2w})
+    return views
+
+
+def mvs_points(n_rays=64, n_samples=20, seed=6):
+    """Ray samples (N, D, 3) around the origin; a fraction falls outside every source frustum / depth range."""
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([0.0, 0.0, -2.5])
+    d = torch.randn(n_rays, 3, generator=g) * torch.tensor([0.35, 0.3, 0.0]) + torch.tensor([0.0, 0.0, 1.0])
+    d = d / d.norm(dim=1, keepdim=True)
+    z = torch.sort(torch.rand(n_rays, n_samples, generator=g) * 5.5 + 0.05, -1)[0]
+    return (o.view(1, 1, 3) + z.unsqueeze(-1) * d.unsqueeze(1)).contiguous()

@@ -7,8 +7,9 @@ mode is BIT-EXACT (indices, counts and positions).
 import pytest
 import torch
 
-from helpers import build_model, conf_of, max_abs, rel_err, state_dict_cpu
+from helpers import build_model, conf_of, load_golden, max_abs, rel_err, state_dict_cpu
 from oracle import volsdf_oracle as O
+import svolsdf_b200._lib as L
 import svolsdf_b200.scene as S
 
 pytestmark = pytest.mark.gpu
@@ -34,7 +35,7 @@ def _points(n, scale=2.4, seed=5, d=3):
 
 def test_library_loaded_is_ours():
     import svolsdf_b200._lib as L
-    assert L.load().svs_abi_version() == 3
+    assert L.load().svs_abi_version() == 4
     assert L.LIB_PATH.endswith('libsvolsdf_b200.so')
 
 
@@ -297,3 +298,61 @@ def test_depth2pts_outside(bmvs):
     pts, dreal = O.depth2pts_outside(o, dd, depth, 3.0)
     p2, d2 = mb.depth2pts_outside(o.to(DEV), dd.to(DEV), depth.to(DEV))
     assert max_abs(p2.cpu(), pts) < 2e-5 and rel_err(d2.cpu(), dreal) < 1e-5
+
+
+# ---- MVS cost lookup (VolOpt.cost_mapping, vsdf.py:382-452) ---------------------------------------
+
+def _mapper(views, img_res, inverse_depth):
+    from svolsdf_b200.mvs import CostMapper
+    ids = [25, 22, 28][:len(views)]
+    return ids, CostMapper([v['cost'][None] for v in views], [v['z_mvs'][None] for v in views], [v['K'] for v in views],
+                           [v['c2w'] for v in views], ids, img_res, inverse_depth=inverse_depth)
+
+
+@pytest.mark.parametrize('tag,own,inv', [('own1_inv', 22, True), ('none_inv', 99, True), ('own0_lin', 25, False)])
+def test_cost_mapping_matches_reference_golden(tag, own, inv):
+    """CUDA kernel vs the outputs of the reference's own cost_mapping (golden made by oracle/make_golden.py)"""
+    g = load_golden('mvs_cost_mapping')
+    views = S.mvs_views(img_res=(72, 96))
+    xyz = torch.from_numpy(g['xyz']).to(DEV)
+    _, cm = _mapper(views, (72, 96), inv)
+    cj, cmv, va = cm(torch.zeros(xyz.shape[:2], device=DEV), torch.tensor([own]), xyz)
+    assert va.dtype == torch.bool and tuple(cj.shape) == tuple(xyz.shape[:2])
+    # the validity tests compare fp32 coordinates with thresholds: identical except where a coordinate is within
+    # rounding of a threshold (the world -> camera product is a matmul in the reference, three FMAs here)
+    mism = (va.cpu().numpy() != g[tag + '_valid'])
+    assert mism.mean() < 2e-3, mism.mean()
+    keep = torch.from_numpy(~mism)
+    assert max_abs(cj.cpu()[keep], torch.from_numpy(g[tag + '_cost_j'])[keep]) < 2e-5
+    assert max_abs(cmv.cpu()[keep], torch.from_numpy(g[tag + '_cost_mvs'])[keep]) < 2e-5
+
+
+@pytest.mark.parametrize('n_rays,n_samples', [(1, 1), (1024, 98), (777, 33)])
+def test_cost_mapping_matches_oracle(n_rays, n_samples):
+    """larger / ragged shapes against the CPU oracle (itself pinned to the reference in test_oracle_vs_golden.py)"""
+    views = S.mvs_views(n_views=3, dz=48, h=72, w=96, img_res=(288, 384), seed=9)
+    xyz = S.mvs_points(n_rays, n_samples, seed=10)
+    ids, cm = _mapper(views, (288, 384), True)
+    cj, cmv, va = cm(torch.zeros(n_rays, n_samples, device=DEV), torch.tensor([ids[2]]), xyz.to(DEV))
+    rj, rm, rv = O.cost_mapping(xyz, views, (288, 384), 2, inverse_depth=True)
+    mism = va.cpu() != rv
+    assert float(mism.float().mean()) < 2e-3
+    keep = ~mism
+    # the synthetic volume is white noise (neighbouring voxels differ by O(0.1)) sampled at 384 x 288 x 48: one ulp of
+    # the normalised coordinate (the reference's world -> camera product is a matmul, here three separately rounded
+    # multiply-adds) moves the lookup by 2e-3 of a voxel, i.e. up to ~2e-4 in the interpolated value
+    assert max_abs(cj.cpu()[keep], rj[keep]) < 5e-4 and max_abs(cmv.cpu()[keep], rm[keep]) < 5e-4
+    assert float((cj.cpu()[keep] - rj[keep]).abs().mean()) < 2e-6
+    if n_rays > 1:
+        assert float(rv.float().mean()) > 0.1
+
+
+def test_cost_mapping_rejects_bad_arguments():
+    from svolsdf_b200.mvs import CostMapper
+    views = S.mvs_views(n_views=1, dz=4, h=6, w=8, img_res=(12, 16))
+    with pytest.raises(L.SvsError):
+        CostMapper([views[0]['cost'][None]] * 9, [views[0]['z_mvs'][None]] * 9, [views[0]['K']] * 9, [views[0]['c2w']] * 9,
+                   list(range(9)), (12, 16))
+    ids, cm = _mapper(views, (1, 16), True)
+    with pytest.raises(L.SvsError):
+        cm(torch.zeros(2, 2, device=DEV), torch.tensor([0]), torch.zeros(2, 2, 3, device=DEV))

@@ -202,3 +202,57 @@ def test_oracle_against_live_reference_if_present():
     assert list(rsd.keys()) == list(osd.keys())
     for k in rsd:
         assert torch.equal(rsd[k], osd[k]), k
+
+
+def _mvs_scene(g):
+    views = S.mvs_views(img_res=(72, 96))
+    chk = sum(float(v[k].double().sum()) for v in views for k in ('cost', 'z_mvs', 'K', 'c2w'))
+    assert abs(chk - float(g['views_checksum'])) < 1e-6 * abs(chk), 'synthetic MVS volumes differ from the ones the golden was made with'
+    return views, torch.from_numpy(g['xyz'])
+
+
+@pytest.mark.parametrize('tag,own,inv', [('own1_inv', 1, True), ('none_inv', -1, True), ('own0_lin', 0, False)])
+def test_cost_mapping_matches_reference(tag, own, inv):
+    """oracle cost_mapping vs the reference's own VolOpt.cost_mapping (vsdf.py:382-452, executed verbatim by
+    oracle/make_golden.py): validity mask identical, interpolated costs to fp32 rounding."""
+    g = load_golden('mvs_cost_mapping')
+    views, xyz = _mvs_scene(g)
+    cj, cm, va = O.cost_mapping(xyz, views, (72, 96), own, inverse_depth=inv)
+    assert bool((va.numpy() == g[tag + '_valid']).all())
+    # costs are sums of up to 8 products of fp32 lerp weights (values <= 1): 2e-5 absolute
+    assert max_abs(cj, g[tag + "_cost_j"]) < 2e-5 and max_abs(cm, g[tag + "_cost_mvs"]) < 2e-5
+    assert float(va.float().mean()) > 0.1 and float(torch.from_numpy(g[tag + '_cost_j']).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize('gce', [1, 0, 0.5])
+@pytest.mark.parametrize('sparse', [0.0, 0.3])
+def test_full_loss_matches_reference(gce, sparse):
+    """oracle VolSDFLoss (rgb + eikonal + generalised-CE MVS + annealed sparsity, loss.py:80-115) vs the reference's"""
+    g = load_golden('mvs_cost_mapping')
+    out = {k: torch.from_numpy(g['loss_in_' + k]) for k in ('rgb_values', 'grad_theta', 'weights', 'depth_values')}
+    out['pj'], out['pi'] = torch.from_numpy(g['own1_inv_cost_j']), torch.from_numpy(g['own1_inv_cost_mvs'])
+    anneal = (1.0 - 25 / 100.0) if sparse else 0.0          # anneal_linearly(iter_step / anneal_rgb, 1, 0), loss.py:8-13,103
+    r = O.volsdf_full_loss(out, torch.from_numpy(g['loss_in_rgb']), eikonal_weight=0.1, mvs_weight=0.5, sparse_weight=sparse,
+                           gce=gce, confi=0.02, anneal_sparse=anneal)
+    for k in ('rgb_loss', 'eikonal_loss', 'mvs_loss', 'sparse_loss', 'loss'):
+        ref = float(g['loss_gce%s_sp%s_%s' % (gce, sparse, k)])
+        assert abs(float(r[k]) - ref) < 1e-6 + 1e-5 * abs(ref), (k, float(r[k]), ref)
+
+
+@pytest.mark.parametrize('gce', [1, 0, 0.5])
+@pytest.mark.parametrize('sparse', [0.0, 0.3])
+def test_loss_module_matches_reference(gce, sparse):
+    """svolsdf_b200.model.loss.VolSDFLoss (the host-side mirror a config's loss_class can name) vs the reference's"""
+    from svolsdf_b200.model.loss import VolSDFLoss
+    g = load_golden('mvs_cost_mapping')
+    out = {k: torch.from_numpy(g['loss_in_' + k]) for k in ('rgb_values', 'grad_theta', 'weights', 'depth_values')}
+    out['pj'], out['pi'] = torch.from_numpy(g['own1_inv_cost_j']), torch.from_numpy(g['own1_inv_cost_mvs'])
+    rgb = torch.from_numpy(g['loss_in_rgb'])
+    L_ = VolSDFLoss('torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=0.5, sparse_weight=sparse, anneal_rgb=100 if sparse else 0,
+                    gce=gce, confi=0.02)
+    L_.iter_step = 25
+    r = L_(out, {'rgb': rgb, 'rgb_smooth': rgb})
+    assert L_.iter_step == 26
+    for k in ('rgb_loss', 'eikonal_loss', 'mvs_loss', 'sparse_loss', 'loss'):
+        ref = float(g['loss_gce%s_sp%s_%s' % (gce, sparse, k)])
+        assert abs(float(r[k]) - ref) < 1e-6 + 1e-5 * abs(ref), (k, float(r[k]), ref)

@@ -86,6 +86,21 @@ for exact in (1, 0):
     ms = timeit(it)
     res.append(('sampler_train_iteration_%s' % ('exact_fp64' if exact else 'fast_fp32'), 2212.0, ms))
 
+# MVS cost lookup (VolOpt.cost_mapping): 3 source views of 48 x 288 x 384 (the paper configuration, vsdf.py:369), 98
+# samples per ray.  Bytes per ray: 98 samples x (12 in + 9 out + 3 views x 16 taps x 4 B gathered from L2-resident volumes)
+if R <= 262144:
+    import svolsdf_b200.scene as S
+    from svolsdf_b200.mvs import CostMapper
+    Rm = min(R, 65536)
+    views = S.mvs_views(n_views=3, dz=48, h=288, w=384, img_res=(1152, 1536), seed=9)
+    cm = CostMapper([v['cost'][None] for v in views], [v['z_mvs'][None] for v in views], [v['K'] for v in views],
+                    [v['c2w'] for v in views], [25, 22, 28], (1152, 1536))
+    xyz = S.mvs_points(Rm, 98, seed=10).to(dev)
+    zt = torch.zeros(Rm, 98, device=dev)
+    own = torch.tensor([22])
+    ms = timeit(lambda: cm(zt, own, xyz)) * (R / Rm)
+    res.append(('cost_mapping_3views', 98 * (21.0 + 3 * 64.0), ms))
+
 out = []
 for name, bpr, ms in res:
     gbs = bpr * R / (ms * 1e-3) / 1e9
