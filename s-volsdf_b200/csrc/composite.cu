@@ -16,18 +16,18 @@ constexpr int kCompWarps = 4;
 
 // per-warp input rows of one ray (z has one pad element for the i + 1 access); `g` is the normals row (forward, eval)
 // or the dL/dweights row (backward)
-template <int C>
+template <int C, int G>
 struct CompRows {
   float z[32 * C + 4];
   float s[32 * C];
   float c[32 * C * 3];
-  float g[32 * C * 3];
+  float g[(G > 0 ? 32 * C * G : 1) + 3];   // G floats per sample: 3 = normals (eval forward), 1 = dL/dweights (backward), 0 = unused
 };
 // two stages per warp: the rows of the warp's NEXT ray land (cp.async, no registers) while the current ray is being
 // composited, so a warp's HBM latency overlaps its own arithmetic; + one output row
-template <int C>
+template <int C, int G>
 struct CompSmem {
-  CompRows<C> in[kCompWarps][2];
+  CompRows<C, G> in[kCompWarps][2];
   float w[kCompWarps][32 * C];
   float o[kCompWarps][32 * C];
 };
@@ -40,8 +40,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // issue the asynchronous copies of one ray's rows (coalesced 4-byte elements: the rows are only 4-byte aligned)
-template <int C>
-__device__ __forceinline__ void issue_rows(CompRows<C>& st, const float* __restrict__ zr, const float* __restrict__ sr,
+template <int C, int G>
+__device__ __forceinline__ void issue_rows(CompRows<C, G>& st, const float* __restrict__ zr, const float* __restrict__ sr,
                                            const float* __restrict__ cr, const float* __restrict__ gr, int n_g, int S, int lane) {
 #pragma unroll
   for (int j = 0; j < C; ++j) {
@@ -58,9 +58,9 @@ __device__ __forceinline__ void issue_rows(CompRows<C>& st, const float* __restr
       if (i < 3 * S) cp_async4(st.c + i, cr + i);
     }
   }
-  if (gr) {
+  if (G > 0 && gr) {
 #pragma unroll
-    for (int j = 0; j < 3 * C; ++j) {
+    for (int j = 0; j < (G > 0 ? G : 1) * C; ++j) {
       const int i = lane + 32 * j;
       if (i < n_g) cp_async4(st.g + i, gr + i);
     }
@@ -147,7 +147,7 @@ __device__ __forceinline__ void warp_suffix_scan(const float (&v)[C], float (&su
   for (int j = 0; j < C; ++j) suf[j] += base;
 }
 
-template <int C, bool FAST>
+template <int C, bool FAST, int G>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
                      const float* __restrict__ normals, const float* __restrict__ beta_param, float beta_min,
@@ -156,7 +156,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
                      float* __restrict__ depth_values, float* __restrict__ normal_map,
                      float* __restrict__ bg_trans) {
   extern __shared__ __align__(16) uint8_t comp_smem_raw[];
-  CompSmem<C>& sm = *reinterpret_cast<CompSmem<C>*>(comp_smem_raw);
+  CompSmem<C, G>& sm = *reinterpret_cast<CompSmem<C, G>*>(comp_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
              tail = flags & SVS_COMP_ZMAX_TAIL;
@@ -164,14 +164,14 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
   // rows shorter than the padded width read as zeros: the copies never touch the pad
   for (int k = 0; k < 2; ++k) {
-    CompRows<C>& st = sm.in[warp][k];
+    CompRows<C, G>& st = sm.in[warp][k];
     for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
     for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
   }
   __syncwarp();
   const float* nrm_rows = normal_map ? normals : nullptr;
   if (ray0 < R)
-    issue_rows<C>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
+    issue_rows<C, G>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
                   nrm_rows ? nrm_rows + ray0 * S * 3 : nullptr, 3 * S, S, lane);
   float n_ds = (depth_scale && ray0 < R) ? __ldg(depth_scale + ray0) : 1.f;
   float n_zmax = (tail && ray0 < R) ? __ldg(z_max + ray0) : 0.f;
@@ -180,7 +180,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     const float ds = n_ds, zmax = n_zmax;
     const int64_t nxt = ray + stride;
     if (nxt < R) {   // the next ray's rows and per-ray scalars are in flight while this ray is composited
-      issue_rows<C>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
+      issue_rows<C, G>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
                     nrm_rows ? nrm_rows + nxt * S * 3 : nullptr, 3 * S, S, lane);
       if (depth_scale) n_ds = __ldg(depth_scale + nxt);
       if (tail) n_zmax = __ldg(z_max + nxt);
@@ -189,7 +189,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       cp_async_wait<0>();
     }
     __syncwarp();
-    const CompRows<C>& in = sm.in[warp][k];
+    const CompRows<C, G>& in = sm.in[warp][k];
     using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C];
     ScanT excl[C];
@@ -273,7 +273,7 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   }
 }
 
-template <int C, bool FAST>
+template <int C, bool FAST, int G>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
                      const float* __restrict__ beta_param, float beta_min,
@@ -282,7 +282,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
                      const float* __restrict__ d_weights, const float* __restrict__ d_bg_trans,
                      float* __restrict__ d_sdf, float* __restrict__ d_rgb, float* __restrict__ d_beta_param) {
   extern __shared__ __align__(16) uint8_t comp_smem_raw[];
-  CompSmem<C>& sm = *reinterpret_cast<CompSmem<C>*>(comp_smem_raw);
+  CompSmem<C, G>& sm = *reinterpret_cast<CompSmem<C, G>*>(comp_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool abs_d = flags & SVS_COMP_ABS_DENSITY, rev = flags & SVS_COMP_REVERSED,
              tail = flags & SVS_COMP_ZMAX_TAIL;
@@ -290,7 +290,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   float dbeta_acc = 0.f;
   const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
   for (int k = 0; k < 2; ++k) {
-    CompRows<C>& st = sm.in[warp][k];
+    CompRows<C, G>& st = sm.in[warp][k];
     for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
     for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
   }
@@ -310,7 +310,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   };
   RayScal nq = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
   if (ray0 < R) {
-    issue_rows<C>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
+    issue_rows<C, G>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
                   d_weights ? d_weights + ray0 * S : nullptr, S, S, lane);
     nq = load_scal(ray0);
   }
@@ -319,7 +319,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     const RayScal cq = nq;
     const int64_t nxt = ray + stride;
     if (nxt < R) {
-      issue_rows<C>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
+      issue_rows<C, G>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
                     d_weights ? d_weights + nxt * S : nullptr, S, S, lane);
       nq = load_scal(nxt);
       cp_async_wait<1>();
@@ -327,7 +327,7 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       cp_async_wait<0>();
     }
     __syncwarp();
-    const CompRows<C>& in = sm.in[warp][k];
+    const CompRows<C, G>& in = sm.in[warp][k];
     const float gr = cq.gr, gg = cq.gg, gb = cq.gb, gdep = cq.gdep, gbt = cq.gbt, ds = cq.ds;
     const float ib = __frcp_rn(beta), i2b2 = __frcp_rn(2.0f * beta * beta);
     using ScanT = typename std::conditional<FAST, float, double>::type;
@@ -521,13 +521,25 @@ extern "C" int svs_composite_forward(const float* z, const float* sdf, const flo
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_fwd", 0.0, (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (normal_map ? 3 : 0)) + 32), st);
   if (flags & SVS_COMP_FAST) {
-    DISPATCH_C(S, (composite_fwd_kernel<C, true><<<comp_grid(composite_fwd_kernel<C, true>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
-                      z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
-                      rgb_values, depth_values, normal_map, bg_trans)));
+    if (normal_map) {
+      DISPATCH_C(S, (composite_fwd_kernel<C, true, 3><<<comp_grid(composite_fwd_kernel<C, true, 3>, sizeof(CompSmem<C, 3>), R), kCompWarps * 32, sizeof(CompSmem<C, 3>), st>>>(
+                        z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                        rgb_values, depth_values, normal_map, bg_trans)));
+    } else {   // training: no normals row -> 1/3 less shared memory, more resident warps
+      DISPATCH_C(S, (composite_fwd_kernel<C, true, 0><<<comp_grid(composite_fwd_kernel<C, true, 0>, sizeof(CompSmem<C, 0>), R), kCompWarps * 32, sizeof(CompSmem<C, 0>), st>>>(
+                        z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                        rgb_values, depth_values, normal_map, bg_trans)));
+    }
   } else {
-    DISPATCH_C(S, (composite_fwd_kernel<C, false><<<comp_grid(composite_fwd_kernel<C, false>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
-                      z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
-                      rgb_values, depth_values, normal_map, bg_trans)));
+    if (normal_map) {
+      DISPATCH_C(S, (composite_fwd_kernel<C, false, 3><<<comp_grid(composite_fwd_kernel<C, false, 3>, sizeof(CompSmem<C, 3>), R), kCompWarps * 32, sizeof(CompSmem<C, 3>), st>>>(
+                        z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                        rgb_values, depth_values, normal_map, bg_trans)));
+    } else {   // training: no normals row -> 1/3 less shared memory, more resident warps
+      DISPATCH_C(S, (composite_fwd_kernel<C, false, 0><<<comp_grid(composite_fwd_kernel<C, false, 0>, sizeof(CompSmem<C, 0>), R), kCompWarps * 32, sizeof(CompSmem<C, 0>), st>>>(
+                        z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
+                        rgb_values, depth_values, normal_map, bg_trans)));
+    }
   }
   SVS_LAUNCH_OK();
   return SVS_OK;
@@ -549,11 +561,11 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   ProfScope ps("composite_bwd", 0.0,
                (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (d_weights ? 1 : 0) + (d_rgb ? 3 : 0)) + 32), st);
   if (flags & SVS_COMP_FAST) {
-    DISPATCH_C(S, (composite_bwd_kernel<C, true><<<comp_grid(composite_bwd_kernel<C, true>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
+    DISPATCH_C(S, (composite_bwd_kernel<C, true, 1><<<comp_grid(composite_bwd_kernel<C, true, 1>, sizeof(CompSmem<C, 1>), R), kCompWarps * 32, sizeof(CompSmem<C, 1>), st>>>(
                       z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                       d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
   } else {
-    DISPATCH_C(S, (composite_bwd_kernel<C, false><<<comp_grid(composite_bwd_kernel<C, false>, sizeof(CompSmem<C>), R), kCompWarps * 32, sizeof(CompSmem<C>), st>>>(
+    DISPATCH_C(S, (composite_bwd_kernel<C, false, 1><<<comp_grid(composite_bwd_kernel<C, false, 1>, sizeof(CompSmem<C, 1>), R), kCompWarps * 32, sizeof(CompSmem<C, 1>), st>>>(
                       z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                       d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));
   }

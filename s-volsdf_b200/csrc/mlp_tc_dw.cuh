@@ -82,7 +82,11 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
         for (int pr = 0; pr < jb.n_pairs; ++pr) {
           const uint8_t* xt = jb.X[pr] + (size_t)t * jb.x_tile_bytes[pr];
           const uint8_t* yt = jb.Y[pr] + (size_t)t * jb.y_tile_bytes[pr];
-          for (int r = 0; r < kTile / kDwRows; ++r, ++seq) {
+          for (int r0 = 0; r0 < kTile / kDwRows; ++r0, ++seq) {
+            // the 32-row slices of a tile may be accumulated in any order: CTAs start at different slices so that at any
+            // moment their 4 KB reads spread over all (address >> 12) & 3 residues instead of marching through the same
+            // one together (ncu: DRAM channels 22 % .. 45 % busy with the lock-step order)
+            const int r = (r0 + split) & (kTile / kDwRows - 1);
             const int slot = seq % kDwStages;
             const uint32_t use = seq / kDwStages;
             mbar_wait(&bars->empty[slot], (use & 1) ^ 1);

@@ -407,6 +407,25 @@ static int launch_dw(DwParams& prm, int64_t P, cudaStream_t st) {
       if (jb.x_blk0 + b < jb.x_kb) ++nxb;
     bytes += (double)prm.n_tiles * jb.n_pairs * (nxb + jb.n_yblk) * kBlk;
   }
+  // hand the CTAs the floor() left over to the jobs with the most work per CTA
+  while (unit < budget) {
+    int best = -1;
+    double worst = 0;
+    for (int j = 0; j < prm.n_jobs; ++j) {
+      const DwJob& jb = prm.job[j];
+      if (jb.n_split >= prm.n_tiles) continue;
+      const double load = cost[j] * (double)cdiv(prm.n_tiles, jb.n_split);
+      if (load > worst) { worst = load; best = j; }
+    }
+    if (best < 0) break;
+    ++prm.job[best].n_split;
+    ++unit;
+  }
+  unit = 0;
+  for (int j = 0; j < prm.n_jobs; ++j) {
+    prm.job[j].unit0 = unit;
+    unit += prm.job[j].n_split;
+  }
   ProfScope ps("mlp_tc_dw", flops, bytes, st);
   tc_dw_kernel<<<unit, 192, kDwSmem, st>>>(prm);
   SVS_LAUNCH_OK();
