@@ -8,9 +8,12 @@
 // tile images with bulk stores straight from the smem tile, and read back the same way ("aux" ring).
 //
 // Warp roles (640 threads): warp 0 weight producer, warp 1 MMA issuer (one elected lane), warp 2 aux producer +
-// TMEM allocation, warps 4..19 epilogue (TMEM lane quarter = warp % 4, 16-column quarter of a block = (warp-4)/4).
-// MMA and epilogue overlap at 64-column granularity: as soon as all epilogue warps have rewritten block c of the
-// tile, the MMAs of the NEXT step that consume block c are issued into the other half of the 512 TMEM columns.
+// TMEM allocation, warp 3 store lane, warps 4..19 epilogue (TMEM lane quarter = warp % 4, 16-column pieces).
+// MMA and epilogue overlap at 16-column granularity: as soon as the four epilogue warps that own a piece of the tile
+// have rewritten it, the one MMA k-step of the NEXT step that consumes those 16 columns is issued into the other
+// half of the 512 TMEM columns.  The forward chains (no aux tiles) run on tc_fwd2_kernel (mlp_tc_fwd2.cuh), which
+// keeps two tiles in flight instead; this kernel serves the chains whose aux ring fills the shared memory.
+// fp32 row-major tensors at the chain boundary (dy, d_feat) are moved coalesced through shared-memory transposes.
 //
 // Chains (math: SURVEY.md Appendix F; reference: volsdf/model/network.py:71-123,170-190 and its autograd graph):
 //   sdf forward        PE -> 8 x softplus layer -> sdf (no-grad) | y = [sdf, features] (+ saved h_1..h_8)
@@ -214,9 +217,6 @@ constexpr float kSpThr = 28.853900817779268f;    // 20 * log2(e): Softplus thres
 // c_lo = ln2/100 * scale, c_hi = scale / (100 log2 e).  softplus(z) >= z, and the capped branch stays at softplus(0.2),
 // so max() selects z exactly where torch's threshold does.
 __device__ __forceinline__ float softplus100_fast(float z, float c_lo, float c_hi) {
-#ifdef SVS_DBG_NOMUFU
-  return fmaxf(z * c_lo, z * c_hi);
-#endif
   float t = z * kSpK1;
   float l = lg2_approx(1.0f + ex2_approx(fminf(t, kSpThr)));
   return fmaxf(l * c_lo, t * c_hi);
@@ -875,9 +875,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           }
           if (writes_a && c < st.next_kb) {
             mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
-#ifndef SVS_DBG_NOSTORE
             st_row16(sA + c * kBlk, m, cq, o);
-#endif
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
