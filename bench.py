@@ -43,6 +43,10 @@ def parse():
     ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
     ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
     ap.add_argument('--no-parity-leg', action='store_true', help='skip the fp32 parity-engine comparison leg (profiling runs)')
+    ap.add_argument('--rng', default='auto', choices=['auto', 'global', 'local'],
+                    help='multi-GPU host random draws: global = every rank draws the whole batch and keeps its rows (sharded run '
+                         'bit-identical per ray to the unsharded one, host work grows with N); local = per-rank streams (data-parallel '
+                         'semantics, host work constant); auto = local when N > 1')
     ap.add_argument('--eager', action='store_true', help='issue every step from Python instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -244,11 +248,13 @@ def run_ours(args):
             reducer.allreduce_(world)
         opt.step()      # gradient clipping to norm 1.0 happens inside the fused step
 
+    rng_mode = 'single' if world == 1 else ('global' if args.rng == 'global' else 'local')
+
     def make_rng():
-        return sdist.ShardedRng(dev, Rg, lo, hi) if world > 1 else RefRng(dev)
+        return sdist.ShardedRng(dev, Rg, lo, hi) if rng_mode == 'global' else RefRng(dev)
 
     # random draws of every step, made in the reference's order and uploaded BEFORE the timed region
-    torch.manual_seed(1234 + 0)
+    torch.manual_seed(1234 + (rank if rng_mode == 'local' else 0))
     tapes = []
     n_prof = 2
     for _ in range(W + max(K, n_prof)):
@@ -337,7 +343,7 @@ def run_ours(args):
     value = Rg / (ms_step * 1e-3)
 
     # ---- end-to-end region: host buffers + host RNG + loss read-back every step ----
-    torch.manual_seed(99)
+    torch.manual_seed(99 + (rank if rng_mode == 'local' else 0))
     for _ in range(3):
         step_e2e()
     barrier()
@@ -442,7 +448,9 @@ def run_ours(args):
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
                    'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)',
-                   'step_mode': step_mode},
+                   'step_mode': step_mode,
+                   'host_rng': {'single': 'reference order, CPU default generator', 'local': 'per-rank CPU streams (seed + rank)',
+                                'global': 'global-batch draws on every rank, rows sliced (sharded == unsharded per ray)'}[rng_mode]},
         'e2e': {'value': Rg / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
