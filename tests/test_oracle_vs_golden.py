@@ -256,3 +256,29 @@ def test_loss_module_matches_reference(gce, sparse):
     for k in ('rgb_loss', 'eikonal_loss', 'mvs_loss', 'sparse_loss', 'loss'):
         ref = float(g['loss_gce%s_sp%s_%s' % (gce, sparse, k)])
         assert abs(float(r[k]) - ref) < 1e-6 + 1e-5 * abs(ref), (k, float(r[k]), ref)
+
+
+@pytest.mark.parametrize('gce', [1, 0, 0.5])
+def test_loss_module_gradients_match_oracle(gce):
+    """the gradients the loss sends back into the kernels' backward (dL/drgb_values, dL/dweights, dL/ddepth_values,
+    dL/dgrad_theta): module vs the oracle restatement, fp64 autograd on both"""
+    from svolsdf_b200.model.loss import VolSDFLoss
+    g = load_golden('mvs_cost_mapping')
+    keys = ('rgb_values', 'grad_theta', 'weights', 'depth_values')
+    rgb = torch.from_numpy(g['loss_in_rgb']).double()
+    grads = []
+    for which in (0, 1):
+        out = {k: torch.from_numpy(g['loss_in_' + k]).double().requires_grad_(True) for k in keys}
+        out['pj'], out['pi'] = torch.from_numpy(g['own1_inv_cost_j']).double(), torch.from_numpy(g['own1_inv_cost_mvs']).double()
+        if which == 0:
+            L_ = VolSDFLoss('torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=0.5, sparse_weight=0.3, anneal_rgb=100, gce=gce, confi=0.02)
+            L_.iter_step = 25
+            loss = L_(out, {'rgb': rgb, 'rgb_smooth': rgb})['loss']
+        else:
+            loss = O.volsdf_full_loss(out, rgb, eikonal_weight=0.1, mvs_weight=0.5, sparse_weight=0.3, gce=gce, confi=0.02,
+                                      anneal_sparse=0.75)['loss']
+        loss.backward()
+        grads.append({k: out[k].grad.clone() for k in keys})
+    for k in keys:
+        assert grads[1][k].abs().max() > 0
+        assert max_abs(grads[0][k], grads[1][k]) < 1e-12, k
