@@ -1,0 +1,20 @@
+"""bench.py's reference arm runs without a GPU (it times the reference's CPU implementation of the path, or the oracle
+port when /root/reference is absent) and prints the contract's JSON line."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                        '--cpu-rays', '32'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'].startswith('rays/sec') and line['unit'] == 'rays/s'
+    assert line['higher_is_better'] is True and line['n_gpus'] == 1 and line['steps'] == 1 and line['value'] > 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['value'] == line['value'] and 'sample' in line['cpu_baseline']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
