@@ -43,6 +43,9 @@ def parse():
     ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
     ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
     ap.add_argument('--no-parity-leg', action='store_true', help='skip the fp32 parity-engine comparison leg (profiling runs)')
+    ap.add_argument('--scene', default='dtu', choices=['dtu', 'bmvs'],
+                    help='train workload: dtu = BASELINE configs[1] (the headline); bmvs = configs[3], VolSDFNetworkBG with the '
+                         'inverted-sphere background networks at 768x576')
     ap.add_argument('--rng', default='auto', choices=['auto', 'global', 'local'],
                     help='multi-GPU host random draws: global = every rank draws the whole batch and keeps its rows (sharded run '
                          'bit-identical per ray to the unsharded one, host work grows with N); local = per-rank streams (data-parallel '
@@ -222,12 +225,17 @@ def run_ours(args):
     Rg = R * world
 
     torch.manual_seed(0)
-    model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
+    bmvs = args.scene == 'bmvs'
+    if bmvs:
+        from svolsdf_b200.model.network_bg import VolSDFNetworkBG
+        model = VolSDFNetworkBG(C.bmvs_model_conf()).to(dev).train().set_engine(engine)
+    else:
+        model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
     # clip_grad_norm_(1.0) + NaN guard + Adam of vsdf.py:214-219 as one fused step (svolsdf_b200.optim.FusedAdam)
     from svolsdf_b200.optim import FusedAdam
     opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
     reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
-    inp_host = S.make_input('dtu', Rg, pixels='perm' if Rg > 4096 else 'random')
+    inp_host = S.make_input(args.scene, Rg, pixels='perm' if Rg > 4096 else 'random')
     gt_host = S.gt_rgb(Rg)
     lo, hi = sdist.shard_range(Rg, rank, world)
     inp_host = sdist.shard_input(inp_host, rank, world)
@@ -438,13 +446,16 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_train_steps(args.cpu_rays, 2, 1)
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-    step_tflops = FLOP_PER_RAY_TRAIN * Rg / (ms_step * 1e-3) / 1e12
+    # BMVS: 128F + 97(6F+3F_r) + 32(3F_bg+3F_br) + 12F per ray
+    step_tflops = (1020432384.0 if bmvs else FLOP_PER_RAY_TRAIN) * Rg / (ms_step * 1e-3) / 1e12
     line = {
         'metric': 'rays/sec (fwd+bwd train step)', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16' if engine == L.ENGINE_TC else 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
-                               'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam', 'rays_per_gpu': R,
+        'config': {'workload': ('BlendedMVS VolSDFNetworkBG train step fwd+bwd+eikonal (BASELINE configs[3]): sampler 128 + main 97 + '
+                                'eikonal 2 SDF evals + 32 inverted-sphere background samples/ray, L1+0.1*eik loss, clip+Adam') if bmvs else
+                               ('DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
+                                'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam'), 'rays_per_gpu': R,
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
                    'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)',

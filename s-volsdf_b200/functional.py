@@ -113,6 +113,7 @@ class SdfOutputsFn(torch.autograd.Function):
         L.call('svs_sdf_outputs_forward', net.desc, ptr(wbuf), ptr(x), P, n_clamped, ptr(y), ptr(sdf),
                ptr(grad), ptr(saved), ptr(ws), net.engine, L.stream())
         ctx.net, ctx.clamp, ctx.P = net, n_clamped, P
+        ctx.want_grad = bool(want_grad)
         if train:
             ctx.save_for_backward(x, y, saved, wbuf)
         if grad is None:
@@ -129,6 +130,10 @@ class SdfOutputsFn(torch.autograd.Function):
         dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
         ws = _f32(max(1, int(lib.svs_sdf_bwd_ws_floats(net.desc, P, net.engine))), device=dev)
         dy, d_sdf, d_grad = _contig(dy), _contig(d_sdf), _contig(d_grad)
+        if not ctx.want_grad:
+            # autograd materialises a zero gradient for the (non-differentiable) dummy `grad` output; passing it on would
+            # run the tangent sweep over the U tiles the forward never wrote (no reverse sweep without want_grad)
+            d_grad = None
         L.call('svs_sdf_outputs_backward', net.desc, ptr(wbuf), ptr(x), P, ctx.clamp, ptr(saved), ptr(y),
                ptr(dy), ptr(d_sdf), ptr(d_grad), ptr(dwbuf), ptr(ws), net.engine, L.stream())
         grads = net.param_grads(wbuf, dwbuf)

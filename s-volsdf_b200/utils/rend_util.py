@@ -24,6 +24,10 @@ def get_sphere_intersections(cam_loc, ray_directions, r=1.0):
     """(R,3),(R,3) -> (R,2) near/far distances.  The reference prints 'BOUNDING SPHERE PROBLEM!' and
     exit()s when a ray misses the sphere (rend_util.py:209-211); here that raises instead."""
     nf, bad = F.sphere_intersections(cam_loc, ray_directions, r)
+    if torch.cuda.is_current_stream_capturing():
+        # a CUDA-graph capture cannot read the flag back; GraphedTrainStep runs (and checks) an eager step with the same
+        # static ray buffers before it captures
+        return nf
     if int(bad.item()) != 0:
         raise RuntimeError('BOUNDING SPHERE PROBLEM!')
     return nf

@@ -249,3 +249,34 @@ def test_full_frame_render_helper_matches_chunked_model_calls():
     for k in ('rgb_values', 'depth_values', 'normal_map'):
         assert torch.equal(got[k], torch.cat([p[k] for p in parts], 0)), k
     assert got['rgb_values'].shape == (300, 3) and len(got['sampler_iters']) == 3
+
+
+@pytest.mark.parametrize('kind', ['dtu', 'bmvs'])
+def test_train_step_reads_no_uninitialised_memory(kind):
+    """The caching allocator's free blocks are filled with NaN before the forward and before the backward: a kernel
+    that reads a workspace / saved tile nobody wrote turns that into non-finite outputs or gradients.  (Found this way:
+    the background SDF net's backward used to run the tangent sweep over never-written U tiles because autograd
+    materialises a zero gradient for the unused `grad` output.)"""
+    def poison():
+        xs = [torch.full((1 << 28,), float('nan'), device=DEV) for _ in range(3)]
+        torch.cuda.synchronize()
+        del xs
+
+    R = 48
+    model = build_model(kind, perturb=True, beta=0.05, device=DEV).train().set_engine(L.ENGINE_TC)
+    inp = {k: v.to(DEV) for k, v in S.make_input(kind, R).items()}
+    gt = S.gt_rgb(R).reshape(-1, 3).to(DEV)
+    poison()
+    torch.manual_seed(321)
+    out = model(inp, fast=1)
+    for k, v in out.items():
+        if torch.is_tensor(v) and v.is_floating_point():
+            assert bool(torch.isfinite(v).all()), k
+    dep = out['depth_values_all'] if kind == 'bmvs' else out['depth_values']
+    loss = (out['rgb_values'] - gt).abs().mean() + 0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean() + \
+        0.05 * out['weights'].pow(2).sum(1).mean() + 0.1 * dep.mean()
+    model.zero_grad()
+    poison()
+    loss.backward()
+    bad = [n for n, p in model.named_parameters() if p.grad is not None and not bool(torch.isfinite(p.grad).all())]
+    assert not bad, bad
