@@ -57,3 +57,30 @@ def test_no_cpu_fallback():
     import torch
     with pytest.raises(L.SvsError):
         L.ptr(torch.zeros(4))
+
+
+def test_argument_validation_and_empty_inputs_need_no_gpu():
+    """error behaviour of the C ABI: bad arguments come back as SVS_ERR_INVALID (-1) with a message, empty inputs are a
+    no-op that returns 0 — both before anything touches the device"""
+    import ctypes as C
+    lib = L.load()
+    p = C.c_void_p(4096)            # never dereferenced: validation and the empty-input return come first
+    # compositor: empty ray set ok, S out of range / missing beta rejected
+    assert lib.svs_composite_forward(p, p, None, None, p, 1e-4, None, None, 0, 98, 0, p, None, None, None, None, None) == 0
+    assert lib.svs_composite_forward(p, p, None, None, p, 1e-4, None, None, 8, 300, 0, p, None, None, None, None, None) < 0
+    assert b'S <= 256' in lib.svs_last_error()
+    assert lib.svs_composite_forward(p, p, None, None, None, 1e-4, None, None, 8, 98, 0, p, None, None, None, None, None) < 0
+    assert lib.svs_composite_backward(p, p, None, p, 1e-4, None, None, 0, 98, 0, None, None, None, None, p, None, None, None) == 0
+    # MVS cost lookup: view count, null volumes, image size
+    v = (L.MvsView * 9)()
+    for i in range(9):
+        v[i].cost, v[i].z_near, v[i].z_far, v[i].Dz, v[i].H, v[i].W = 4096, 4096, 4096, 4, 6, 8
+    assert lib.svs_cost_mapping(p, 0, 20, v, 3, 72, 96, 1, p, p, p, None) == 0          # no samples
+    assert lib.svs_cost_mapping(p, 4, 20, v, 9, 72, 96, 1, p, p, p, None) < 0           # > 8 views
+    assert b'n_views' in lib.svs_last_error()
+    assert lib.svs_cost_mapping(p, 4, 20, v, 0, 72, 96, 1, p, p, p, None) < 0
+    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 1, 96, 1, p, p, p, None) < 0            # degenerate image
+    v[1].cost = None
+    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 72, 96, 1, p, p, p, None) < 0
+    assert b'view 1' in lib.svs_last_error()
+    assert lib.svs_cost_mapping(None, 4, 20, v, 3, 72, 96, 1, p, p, p, None) < 0
