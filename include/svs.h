@@ -39,8 +39,13 @@ typedef enum {
 /* arithmetic engine of the MLP kernels */
 typedef enum {
   SVS_ENGINE_FP32 = 0, /* fp32 SIMT FFMA tiles: parity mode (rgb/depth <= 1e-3 vs the reference) */
-  SVS_ENGINE_TC = 1    /* tcgen05.mma kind::f16: fp16 operands (10-bit mantissa, TF32-class), fp32 TMEM accumulators;
-                          activations stay in shared memory across the layers of a chain (mlp_tc.cuh) */
+  SVS_ENGINE_TC = 1,   /* tcgen05.mma kind::f16: fp16 operands (10-bit mantissa, TF32-class), fp32 TMEM accumulators;
+                          activations stay in shared memory across the layers of a chain (mlp_tc.cuh).  Fastest; sdf
+                          ~1e-3, i.e. outside the 1e-3 depth contract */
+  SVS_ENGINE_TC_SPLIT = 2 /* tcgen05 with split operands in every FORWARD chain (fp16 hi + fp16 lo halves of activations
+                          and weights, 3 MMAs per layer, mlp_tc_fwd3.cuh): sdf / rgb / depth at fp32-class accuracy
+                          (<= 1e-5 vs the reference), ReLU masks as the reference; backward chains as SVS_ENGINE_TC
+                          (parameter gradients <= 5e-3 relative).  The tensor-core mode that meets the parity contract. */
 } svs_engine;
 
 typedef enum { SVS_NET_SDF = 0, SVS_NET_RENDER = 1 } svs_net_kind;

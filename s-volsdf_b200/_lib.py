@@ -11,7 +11,7 @@ import os
 import torch
 
 SVS_MAX_LAYERS = 12
-ENGINE_FP32, ENGINE_TC = 0, 1
+ENGINE_FP32, ENGINE_TC, ENGINE_TC_SPLIT = 0, 1, 2
 NET_SDF, NET_RENDER = 0, 1
 RENDER_IDR, RENDER_NERF = 0, 1
 COMP_ABS_DENSITY, COMP_REVERSED, COMP_ZMAX_TAIL, COMP_FAST = 1, 2, 4, 8

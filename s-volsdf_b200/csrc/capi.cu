@@ -51,7 +51,7 @@ void prof_end(int id, cudaStream_t st) {
 extern "C" const char* svs_last_error(void) { return svs::g_err; }
 extern "C" int svs_abi_version(void) { return SVS_ABI_VERSION; }
 extern "C" int svs_has_engine(int engine) {
-  return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC;
+  return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC || engine == SVS_ENGINE_TC_SPLIT;
 }
 
 extern "C" int64_t svs_launch_count(void) { return svs::g_launches; }

@@ -127,24 +127,24 @@ __device__ __forceinline__ T warp_excl_scan(const float (&v)[C], T (&excl)[C], i
 // suffix sums suf[j] = sum of the elements AFTER element (lane, j) in the lane-contiguous order: a reverse scan, so
 // the last element's suffix is exactly 0 and nothing cancels (a `total - prefix` in fp32 leaves a 1e-7 residue that
 // the reference's last interval of 1e10 would blow up in d sigma)
-template <int C>
+template <int C, typename T>
 __device__ __forceinline__ void warp_suffix_scan(const float (&v)[C], float (&suf)[C], int lane) {
-  float run = 0.f;
+  T run = 0, part[C];
 #pragma unroll
   for (int j = C - 1; j >= 0; --j) {
-    suf[j] = run;
-    run += v[j];
+    part[j] = run;
+    run += (T)v[j];
   }
-  float incl = run;
+  T incl = run;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    float t = __shfl_down_sync(0xffffffffu, incl, o);
+    T t = __shfl_down_sync(0xffffffffu, incl, o);
     if (lane + o < 32) incl += t;
   }
-  float base = __shfl_down_sync(0xffffffffu, incl, 1);   // total of the lanes after this one
-  if (lane == 31) base = 0.f;
+  T base = __shfl_down_sync(0xffffffffu, incl, 1);   // total of the lanes after this one
+  if (lane == 31) base = 0;
 #pragma unroll
-  for (int j = 0; j < C; ++j) suf[j] += base;
+  for (int j = 0; j < C; ++j) suf[j] = (float)(part[j] + base);
 }
 
 template <int C, bool FAST, int G>
@@ -383,19 +383,18 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
       what[j] = v;
       ww[j] = v * w[j];
     }
-    // suffix sums: sum_{k>i} what_k w_k = total - inclusive prefix
-    ScanT excl2[C];
-    ScanT tot2 = 0;
+    // suffix sums sum_{k>i} what_k w_k as a reverse scan (fp64 in the canonical mode).  NOT total - inclusive prefix: the
+    // residue of that cancellation, times the reference's last interval of 1e10, put 8 % of error into dL/dbeta of a
+    // 1024-ray batch (tools/dbeta_debug.py)
     float suf[C];
-    if (FAST) warp_suffix_scan<C>(ww, suf, lane);
-    else tot2 = warp_excl_scan<C, ScanT>(ww, excl2, lane);
+    warp_suffix_scan<C, ScanT>(ww, suf, lane);
     const float bgt = tail ? exp_t<FAST>(-(float)total) : 0.f;
     float dbeta = 0.f;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       if (i < S) {
-        float suffix = FAST ? suf[j] : (float)(tot2 - excl2[j] - (ScanT)ww[j]);
+        float suffix = suf[j];
         float dE = what[j] * Te[j] - suffix - gbt * bgt;
         float dsig = dl[j] * dE;
         float dsdf;

@@ -388,12 +388,14 @@ using namespace svs;
 // C ABI
 // ====================================================================================================
 
-static bool engine_ok(int engine) { return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC; }
+static bool engine_ok(int engine) { return engine == SVS_ENGINE_FP32 || engine == SVS_ENGINE_TC || engine == SVS_ENGINE_TC_SPLIT; }
+static bool is_tc(int engine) { return engine == SVS_ENGINE_TC || engine == SVS_ENGINE_TC_SPLIT; }
+static bool is_split(int engine) { return engine == SVS_ENGINE_TC_SPLIT; }
 
 extern "C" int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) return tc::wbuf_floats_tc(d, lo);
+  if (is_tc(engine)) return tc::wbuf_floats_tc(d, lo, is_split(engine));
   return lo.total;
 }
 
@@ -410,7 +412,7 @@ extern "C" int svs_mlp_prepare(const svs_mlp_desc* d, const svs_mlp_params* p, f
   fill_pack(lo, p, nullptr, &a);
   pack_weights_kernel<<<(unsigned)cdiv(a.row0[lo.L], 4), 128, 0, (cudaStream_t)stream>>>(a, wbuf);
   SVS_LAUNCH_OK();
-  if (engine == SVS_ENGINE_TC) SVS_TRY(tc::pack_images(d, lo, wbuf, (cudaStream_t)stream));
+  if (is_tc(engine)) SVS_TRY(tc::pack_images(d, lo, wbuf, (cudaStream_t)stream, is_split(engine)));
   return SVS_OK;
 }
 
@@ -453,7 +455,7 @@ extern "C" int32_t svs_sdf_ldy(const svs_mlp_desc* d) {
 extern "C" int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) {
+  if (is_tc(engine)) {
     tc::SdfSaved sv;
     tc::map_sdf_saved(lo, P, nullptr, &sv);
     return sv.bytes / 4;
@@ -464,7 +466,7 @@ extern "C" int64_t svs_sdf_saved_floats(const svs_mlp_desc* d, int64_t P, int en
 extern "C" int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_grad, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) return with_grad ? svs_sdf_saved_floats(d, P, engine) : 4;
+  if (is_tc(engine)) return with_grad ? svs_sdf_saved_floats(d, P, engine) : 4;
   if (with_grad) return svs_sdf_saved_floats(d, P, engine) + P * 2 * (int64_t)lo.ld0;
   return P * ((int64_t)lo.ld0 + 2 * (int64_t)lo.H + lo.ldy);
 }
@@ -472,7 +474,7 @@ extern "C" int64_t svs_sdf_ws_floats(const svs_mlp_desc* d, int64_t P, int with_
 extern "C" int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) {
+  if (is_tc(engine)) {
     tc::SdfBwdWs bw;
     tc::map_sdf_bwd(lo, P, nullptr, &bw);
     return bw.bytes / 4;
@@ -496,7 +498,7 @@ extern "C" int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const f
   SVS_CHECK_ARG(wbuf && x && ws && (y || sdf) && P >= 0, "svs_sdf_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == SVS_ENGINE_TC) return tc::sdf_forward(d, lo, wbuf, x, P, y, sdf, st);
+  if (is_tc(engine)) return tc::sdf_forward(d, lo, wbuf, x, P, y, sdf, st, is_split(engine));
   float* A0 = ws;
   float* B[2] = {A0 + P * lo.ld0, A0 + P * lo.ld0 + P * lo.H};
   float* Y = y ? y : (B[1] + P * lo.H);
@@ -559,9 +561,9 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
   SVS_CHECK_ARG(wbuf && x && y && ws && P >= 0, "svs_sdf_outputs_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == SVS_ENGINE_TC) {
+  if (is_tc(engine)) {
     if (!grad && !saved) {
-      SVS_TRY(tc::sdf_forward(d, lo, wbuf, x, P, y, nullptr, st));
+      SVS_TRY(tc::sdf_forward(d, lo, wbuf, x, P, y, nullptr, st, is_split(engine)));
       if (sdf) {
         sdf_clamp_kernel<<<blocks_for(P), 256, 0, st>>>(x, y, lo.ldy, P, d->d_in, d->sphere_radius, d->sphere_scale,
                                                         n_clamped, sdf);
@@ -569,7 +571,7 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
       }
       return SVS_OK;
     }
-    return tc::sdf_outputs_forward(d, lo, wbuf, x, P, n_clamped, y, sdf, grad, saved ? (void*)saved : (void*)ws, st);
+    return tc::sdf_outputs_forward(d, lo, wbuf, x, P, n_clamped, y, sdf, grad, saved ? (void*)saved : (void*)ws, st, is_split(engine));
   }
   SdfBuffers b;
   float* scratch = ws;
@@ -658,7 +660,7 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
   SVS_CHECK_ARG(wbuf && x && saved && y && dwbuf && ws && P >= 0, "svs_sdf_outputs_backward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == SVS_ENGINE_TC)
+  if (is_tc(engine))
     return tc::sdf_outputs_backward(d, lo, wbuf, x, P, n_clamped, saved, y, dy, d_sdf, d_grad, dwbuf, ws, st);
   const int L = lo.L;
   SdfBuffers b;
@@ -769,7 +771,7 @@ static int check_render(const svs_mlp_desc* d, const Layout& lo, int engine, int
 extern "C" int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) {
+  if (is_tc(engine)) {
     tc::WImages wi;
     if (tc::make_wimages(d, lo, &wi, nullptr, nullptr) != SVS_OK) return -1;
     tc::RenderSaved sv;
@@ -782,7 +784,7 @@ extern "C" int64_t svs_render_saved_floats(const svs_mlp_desc* d, int64_t P, int
 extern "C" int64_t svs_render_ws_floats(const svs_mlp_desc* d, int64_t P, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;
-  if (engine == SVS_ENGINE_TC) {
+  if (is_tc(engine)) {
     tc::RenderWs rw;
     tc::map_render_ws(lo, P, nullptr, &rw);
     return rw.bytes / 4;
@@ -803,8 +805,8 @@ extern "C" int svs_render_forward(const svs_mlp_desc* d, const float* wbuf, cons
   SVS_CHECK_ARG(ld_feat >= F, "svs_render_forward: ld_feat %d < feature width %d", ld_feat, F);
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == SVS_ENGINE_TC)
-    return tc::render_forward(d, lo, wbuf, points, view_dirs, normals, feat, ld_feat, P, rgb, saved, st);
+  if (is_tc(engine))
+    return tc::render_forward(d, lo, wbuf, points, view_dirs, normals, feat, ld_feat, P, rgb, saved, st, is_split(engine));
   const int L = lo.L;
   float* RIN = saved;
   float* Bv[SVS_MAX_LAYERS];
@@ -850,7 +852,7 @@ extern "C" int svs_render_backward(const svs_mlp_desc* d, const float* wbuf, int
   SVS_CHECK_ARG(wbuf && saved && rgb && d_rgb && dwbuf && ws && P >= 0, "svs_render_backward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine == SVS_ENGINE_TC)
+  if (is_tc(engine))
     return tc::render_backward(d, lo, wbuf, P, saved, rgb, d_rgb, d_normals, d_feat, ld_dfeat, dwbuf, ws, st);
   const int L = lo.L;
   const float* RIN = saved;

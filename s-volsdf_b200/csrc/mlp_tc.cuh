@@ -88,6 +88,7 @@ constexpr int32_t TC_QFILL = 2;    // step flag: fill pad columns of A' with (J_
 
 struct TcStep {
   const uint8_t* w;    // KB blocks of n_pad x 128 bytes
+  const uint8_t* w_lo; // split-operand chains (SVS_ENGINE_TC_SPLIT, mlp_tc_fwd3.cuh): the image of W - fp16(W), same geometry
   const float* bias;   // fp32[n_valid] or nullptr
   int32_t KB, n_pad, n_valid, epi;
   float scale, hscale;
@@ -115,6 +116,7 @@ struct TcChain {
   const float* pro_vec;                         // PRO_LOAD_ULAST: fp32 row vector (W_last[0,:])
   int64_t P;
   int32_t n_tiles;
+  int32_t split;                                // 1: forward chain with hi + lo operands (tc_fwd3_kernel)
   // geometry of the SDF net input
   const float* x;
   int32_t d_in, n_freqs;

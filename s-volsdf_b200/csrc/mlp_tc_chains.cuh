@@ -16,8 +16,10 @@ static void sdf_geometry(TcChain* ch, const svs_mlp_desc* d, const float* x, int
 }
 
 // forward layers 0..L-2 (softplus); saves h_{l+1} when `sv` is given
-static void add_sdf_forward_steps(TcChain* ch, const Layout& lo, const WImages& wi, const float* wbuf, const SdfSaved* sv) {
+static void add_sdf_forward_steps(TcChain* ch, const Layout& lo, const WImages& wi, const float* wbuf, const SdfSaved* sv,
+                                  bool split) {
   const uint8_t* reg = wimg_region(lo, wbuf);
+  ch->split = split ? 1 : 0;
   ch->prologue = PRO_PE;
   ch->pro_kb = kb_of(lo.in[0]);
   if (sv) {
@@ -27,6 +29,7 @@ static void add_sdf_forward_steps(TcChain* ch, const Layout& lo, const WImages& 
   for (int l = 0; l < lo.L - 1; ++l) {
     TcStep s = make_step(reg + wi.fwd[l], wbuf + lo.boff[l], wi.fwd_kb[l], wi.fwd_npad[l], lo.out[l], EP_SOFTPLUS);
     s.next_kb = kb_of(lo.in[l + 1]);
+    if (split) s.w_lo = reg + wi.fwd_lo[l];
     if (l + 1 == lo.skip) {
       s.scale = kInvSqrt2;
       s.flags = TC_PEFILL;
@@ -41,25 +44,29 @@ static void add_sdf_forward_steps(TcChain* ch, const Layout& lo, const WImages& 
 
 // y (P, ldy) and/or clamped sdf (P) without saving anything: ImplicitNetwork.forward / get_sdf_vals under no_grad
 static int sdf_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbuf, const float* x, int64_t P, float* y,
-                       float* sdf, cudaStream_t st) {
+                       float* sdf, cudaStream_t st, bool split) {
   WImages wi;
-  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr));
+  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr, split));
   const uint8_t* reg = wimg_region(lo, wbuf);
   const int L = lo.L;
   TcChain ch;
   init_chain(&ch);
   sdf_geometry(&ch, d, x, P, P);
-  add_sdf_forward_steps(&ch, lo, wi, wbuf, nullptr);
+  add_sdf_forward_steps(&ch, lo, wi, wbuf, nullptr, split);
   ch.y = y;
   ch.ldy = lo.ldy;
   ch.sdf = sdf;
   if (sdf) {
-    ch.st[ch.n_steps++] = make_step(reg + wi.fwd_sdf, wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], 16, 1, EP_SDF);
+    TcStep s0 = make_step(reg + wi.fwd_sdf, wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], 16, 1, EP_SDF);
+    if (split) s0.w_lo = reg + wi.fwd_sdf_lo;
+    ch.st[ch.n_steps++] = s0;
   }
   if (y) {
     TcStep s0 = make_step(reg + wi.fwd_sdf, wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], 16, 1, EP_Y);
+    if (split) s0.w_lo = reg + wi.fwd_sdf_lo;
     ch.st[ch.n_steps++] = s0;
     TcStep s1 = make_step(reg + wi.fwd[L - 1], wbuf + lo.boff[L - 1] + 1, wi.fwd_kb[L - 1], wi.fwd_npad[L - 1], lo.out[L - 1] - 1, EP_Y);
+    if (split) s1.w_lo = reg + wi.fwd_lo[L - 1];
     s1.y_col = 1;
     ch.st[ch.n_steps++] = s1;
   }
@@ -68,9 +75,9 @@ static int sdf_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbu
 
 // get_outputs()/gradient(): y, clamped sdf, d sdf/dx; `saved` keeps A0, h_1..h_{L-1}, U_0..U_{L-2} for the backward
 static int sdf_outputs_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbuf, const float* x, int64_t P,
-                               int64_t clamp, float* y, float* sdf, float* grad, void* saved, cudaStream_t st) {
+                               int64_t clamp, float* y, float* sdf, float* grad, void* saved, cudaStream_t st, bool split) {
   WImages wi;
-  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr));
+  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr, split));
   const uint8_t* reg = wimg_region(lo, wbuf);
   const int L = lo.L;
   SdfSaved sv;
@@ -80,11 +87,14 @@ static int sdf_outputs_forward(const svs_mlp_desc* d, const Layout& lo, const fl
     TcChain ch;
     init_chain(&ch);
     sdf_geometry(&ch, d, x, P, clamp);
-    add_sdf_forward_steps(&ch, lo, wi, wbuf, &sv);
+    add_sdf_forward_steps(&ch, lo, wi, wbuf, &sv, split);
     ch.y = y;
     ch.ldy = lo.ldy;
-    ch.st[ch.n_steps++] = make_step(reg + wi.fwd_sdf, wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], 16, 1, EP_Y);
+    TcStep s0 = make_step(reg + wi.fwd_sdf, wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], 16, 1, EP_Y);
+    if (split) s0.w_lo = reg + wi.fwd_sdf_lo;
+    ch.st[ch.n_steps++] = s0;
     TcStep s1 = make_step(reg + wi.fwd[L - 1], wbuf + lo.boff[L - 1] + 1, wi.fwd_kb[L - 1], wi.fwd_npad[L - 1], lo.out[L - 1] - 1, EP_Y);
+    if (split) s1.w_lo = reg + wi.fwd_lo[L - 1];
     s1.y_col = 1;
     ch.st[ch.n_steps++] = s1;
     SVS_TRY(launch_chain(ch, "mlp_tc_sdf_fwd", chain_flops(ch), 0.0, st));
@@ -283,9 +293,9 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
 // ---------------------------------------------------------------------------------------------------------------
 static int render_forward(const svs_mlp_desc* d, const Layout& lo, const float* wbuf, const float* points,
                           const float* view_dirs, const float* normals, const float* feat, int ld_feat, int64_t P,
-                          float* rgb, void* saved, cudaStream_t st) {
+                          float* rgb, void* saved, cudaStream_t st, bool split) {
   WImages wi;
-  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr));
+  SVS_TRY(make_wimages(d, lo, &wi, nullptr, nullptr, split));
   const uint8_t* reg = wimg_region(lo, wbuf);
   const int L = lo.L;
   RenderSaved sv;
@@ -298,6 +308,7 @@ static int render_forward(const svs_mlp_desc* d, const Layout& lo, const float* 
   ch.idr = d->render_mode == SVS_RENDER_IDR;
   ch.F = wi.F;
   ch.rgb = rgb;
+  ch.split = split ? 1 : 0;
   ch.prologue = PRO_RENDER_IN;
   ch.pro_kb = wi.F / 64 + 1;
   int ni = 0;
@@ -306,11 +317,16 @@ static int render_forward(const svs_mlp_desc* d, const Layout& lo, const float* 
   for (int l = 0; l < L - 1; ++l) {
     TcStep s = make_step(reg + wi.fwd[l], wbuf + lo.boff[l], wi.fwd_kb[l], wi.fwd_npad[l], lo.out[l], EP_RELU);
     s.next_kb = kb_of(lo.in[l + 1]);
+    if (split) s.w_lo = reg + wi.fwd_lo[l];
     ch.img[ni] = timg(sv.H[l + 1]);
     s.save = ni++;
     ch.st[ch.n_steps++] = s;
   }
-  ch.st[ch.n_steps++] = make_step(reg + wi.fwd[L - 1], wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], wi.fwd_npad[L - 1], lo.out[L - 1], EP_RGB);
+  {
+    TcStep s = make_step(reg + wi.fwd[L - 1], wbuf + lo.boff[L - 1], wi.fwd_kb[L - 1], wi.fwd_npad[L - 1], lo.out[L - 1], EP_RGB);
+    if (split) s.w_lo = reg + wi.fwd_lo[L - 1];
+    ch.st[ch.n_steps++] = s;
+  }
   return launch_chain(ch, "mlp_tc_render_fwd", chain_flops(ch), 0.0, st);
 }
 

@@ -23,6 +23,7 @@
 #endif
 #include "mlp_tc_dw.cuh"
 #include "mlp_tc_fwd2.cuh"
+#include "mlp_tc_fwd3.cuh"
 
 namespace svs {
 namespace tc {
@@ -35,6 +36,7 @@ struct WImages {
   int64_t fwd[SVS_MAX_LAYERS];   // B[n = out][k = in]   (last SDF layer: the feature rows 1..out-1)
   int64_t bwd[SVS_MAX_LAYERS];   // B[n = in][k = out]   (rendering layer 0: the feature columns)
   int64_t fwd_sdf;               // SDF last layer, row 0 padded to 16 rows
+  int64_t fwd_lo[SVS_MAX_LAYERS], fwd_sdf_lo;   // split engine: images of W - fp16(W) (behind all regular images)
   int64_t bwd_small;             // rendering layer 0: the non-feature input columns
   int fwd_npad[SVS_MAX_LAYERS], fwd_kb[SVS_MAX_LAYERS];
   int bwd_npad[SVS_MAX_LAYERS], bwd_kb[SVS_MAX_LAYERS];
@@ -50,15 +52,16 @@ struct PackImg {
   int transpose;      // 0: value(r, c) = W[r0 + r][cmap(c)] ; 1: value(r, c) = W[c][cmap(r0 + r)]
   int r0, nr, nc;     // row offset / valid rows / valid cols (in image coordinates)
   int rot_f, rot_s;   // input-column rotation: image input index i -> W column (i < rot_f ? i + rot_s : i - rot_f)
+  int lo;             // 1: store W - fp16(W) (the low half of the split operand) instead of fp16(W)
 };
 
-static int make_wimages(const svs_mlp_desc* d, const Layout& lo, WImages* wi, PackImg* list, int* n_list) {
+static int make_wimages(const svs_mlp_desc* d, const Layout& lo, WImages* wi, PackImg* list, int* n_list, bool split = false) {
   memset(wi, 0, sizeof(*wi));
   int64_t off = 0;
   int n = 0;
   auto add = [&](int n_pad, int kb, int layer, int transpose, int r0, int nr, int nc, int rot_f, int rot_s) {
     int64_t o = off;
-    if (list) list[n] = PackImg{(long long)o, n_pad, kb, layer, transpose, r0, nr, nc, rot_f, rot_s};
+    if (list) list[n] = PackImg{(long long)o, n_pad, kb, layer, transpose, r0, nr, nc, rot_f, rot_s, 0};
     ++n;
     off += round_up((int64_t)n_pad * kb * 128, 1024);
     return o;
@@ -110,13 +113,39 @@ static int make_wimages(const svs_mlp_desc* d, const Layout& lo, WImages* wi, Pa
                     "rendering layer %d (%d -> %d) too wide for the tcgen05 engine", l, lo.in[l], lo.out[l]);
     }
   }
+  // low halves of the forward images (split engine only), appended so that the offsets above do not depend on `split`
+  {
+    auto add_lo = [&](int n_pad, int kb, int layer, int r0, int nr, int nc, int rot_f, int rot_s) {
+      int64_t o = off;
+      if (split) {
+        if (list) list[n] = PackImg{(long long)o, n_pad, kb, layer, 0, r0, nr, nc, rot_f, rot_s, 1};
+        ++n;
+        off += round_up((int64_t)n_pad * kb * 128, 1024);
+      }
+      return o;
+    };
+    if (d->kind == SVS_NET_SDF) {
+      for (int l = 0; l < L; ++l) {
+        if (l < L - 1) {
+          wi->fwd_lo[l] = add_lo(wi->fwd_npad[l], wi->fwd_kb[l], l, 0, lo.out[l], lo.in[l], 0, 0);
+        } else {
+          wi->fwd_lo[l] = add_lo(wi->fwd_npad[l], wi->fwd_kb[l], l, 1, lo.out[l] - 1, lo.in[l], 0, 0);
+          wi->fwd_sdf_lo = add_lo(16, wi->fwd_kb[l], l, 0, 1, lo.in[l], 0, 0);
+        }
+      }
+    } else {
+      for (int l = 0; l < L; ++l)
+        wi->fwd_lo[l] = add_lo(wi->fwd_npad[l], wi->fwd_kb[l], l, 0, lo.out[l], (l == 0) ? wi->F + wi->n_small : lo.in[l],
+                               (l == 0) ? wi->F : 0, (l == 0) ? wi->n_small : 0);
+    }
+  }
   wi->bytes = off;
   if (n_list) *n_list = n;
   return SVS_OK;
 }
 
 struct PackArgsTc {
-  PackImg img[3 * SVS_MAX_LAYERS];
+  PackImg img[4 * SVS_MAX_LAYERS + 2];
   int woff_ld[SVS_MAX_LAYERS];
   long long woff[SVS_MAX_LAYERS];
   int in[SVS_MAX_LAYERS], out[SVS_MAX_LAYERS];
@@ -137,25 +166,27 @@ __global__ void pack_images_kernel(const PackArgsTc a, const float* __restrict__
       if (im.rot_f > 0) i = (i < im.rot_f) ? i + im.rot_s : i - im.rot_f;
       if (o < a.out[l] && i < a.in[l]) v = wbuf[a.woff[l] + (long long)o * a.woff_ld[l] + i];
     }
-    *reinterpret_cast<__half*>(region + im.dst + img_off(r, c, im.n_pad)) = __float2half_rn(v);
+    __half hv = __float2half_rn(v);
+    if (im.lo) hv = __float2half_rn(v - __half2float(hv));
+    *reinterpret_cast<__half*>(region + im.dst + img_off(r, c, im.n_pad)) = hv;
   }
 }
 
-static int64_t wbuf_floats_tc(const svs_mlp_desc* d, const Layout& lo) {
+static int64_t wbuf_floats_tc(const svs_mlp_desc* d, const Layout& lo, bool split) {
   WImages wi;
-  if (make_wimages(d, lo, &wi, nullptr, nullptr) != SVS_OK) return -1;
+  if (make_wimages(d, lo, &wi, nullptr, nullptr, split) != SVS_OK) return -1;
   return round_up(lo.total, 256) + wi.bytes / 4;
 }
 static inline uint8_t* wimg_region(const Layout& lo, const float* wbuf) {
   return reinterpret_cast<uint8_t*>(const_cast<float*>(wbuf) + round_up(lo.total, 256));
 }
 
-static int pack_images(const svs_mlp_desc* d, const Layout& lo, float* wbuf, cudaStream_t st) {
+static int pack_images(const svs_mlp_desc* d, const Layout& lo, float* wbuf, cudaStream_t st, bool split) {
   WImages wi;
   PackArgsTc a;
   memset(&a, 0, sizeof(a));
   int n = 0;
-  SVS_TRY(make_wimages(d, lo, &wi, a.img, &n));
+  SVS_TRY(make_wimages(d, lo, &wi, a.img, &n, split));
   for (int l = 0; l < lo.L; ++l) {
     a.woff[l] = lo.woff[l];
     a.woff_ld[l] = lo.ldi[l];
@@ -308,6 +339,12 @@ static int launch_chain(TcChain& ch, const char* name, double flops, double byte
   const int grid = ch.n_tiles < num_sms() ? ch.n_tiles : num_sms();
   if (bytes <= 0.0) bytes = chain_bytes(ch);
   ProfScope ps(name, flops, bytes, st);
+  if (ch.split) {
+    if (!fwd3_supports(ch)) { set_error("launch_chain: chain not supported by the split-operand forward kernel"); return SVS_ERR_UNSUPPORTED; }
+    SVS_TRY(launch_fwd3(ch, grid, st));
+    SVS_LAUNCH_OK();
+    return SVS_OK;
+  }
   switch (ch.prologue) {
     case PRO_PE:
 #ifndef SVS_TC_NO_FWD2

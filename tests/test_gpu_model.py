@@ -5,10 +5,14 @@ import torch
 
 from helpers import build_model, conf_of, load_golden, max_abs, model_from_golden, rel_err, state_dict_cpu
 from oracle import volsdf_oracle as O
+import svolsdf_b200._lib as L
 import svolsdf_b200.scene as S
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
+# the two engines that claim the parity contract (rgb / depth <= 1e-3, parameter gradients <= 1e-2): fp32 SIMT and tcgen05
+# with split operands in the forward chains (the benchmarked engine)
+PARITY_ENGINES = [pytest.param(L.ENGINE_FP32, id='fp32'), pytest.param(L.ENGINE_TC_SPLIT, id='tc_split')]
 
 
 def _to_dev(inp):
@@ -101,11 +105,13 @@ def test_sampler_fast_mode_close():
 # model forward / backward
 # ------------------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize('engine', PARITY_ENGINES)
 @pytest.mark.parametrize('name', ['dtu_eval_r64', 'dtu_eval_r32_beta001', 'bmvs_eval_r32'])
-def test_eval_forward_vs_reference_golden(name):
-    """End to end against the REFERENCE's recorded outputs (north_star: rgb/depth max-abs <= 1e-3, fp32 mode)."""
+def test_eval_forward_vs_reference_golden(name, engine):
+    """End to end (own sampler, no injected positions) against the REFERENCE's recorded outputs (north_star: rgb/depth
+    max-abs <= 1e-3)."""
     g = load_golden(name)
-    model = model_from_golden(g, DEV).eval()
+    model = model_from_golden(g, DEV).eval().set_engine(engine)
     kind, R = str(g['meta/kind']), int(g['meta/n_rays'])
     torch.manual_seed(123)
     out = model(_to_dev(S.make_input(kind, R)))
@@ -128,11 +134,12 @@ def test_eval_forward_vs_reference_golden(name):
     assert abs(float(out['weights'].sum()) - float(g['out/weights'].sum())) < 1e-2 * R
 
 
+@pytest.mark.parametrize('engine', PARITY_ENGINES)
 @pytest.mark.parametrize('name', ['dtu_train_r64', 'dtu_train_r64_pert', 'bmvs_train_r32'])
-def test_train_step_vs_reference_golden(name):
+def test_train_step_vs_reference_golden(name, engine):
     """Forward + VolSDFLoss + backward against the reference's recorded loss and gradient fingerprints."""
     g = load_golden(name)
-    model = model_from_golden(g, DEV).train()
+    model = model_from_golden(g, DEV).train().set_engine(engine)
     kind, R = str(g['meta/kind']), int(g['meta/n_rays'])
     torch.manual_seed(123)
     out = model(_to_dev(S.make_input(kind, R)), fast=1)
@@ -161,11 +168,12 @@ def test_train_step_vs_reference_golden(name):
     assert not bad, bad[:6]
 
 
+@pytest.mark.parametrize('engine', PARITY_ENGINES)
 @pytest.mark.parametrize('kind', ['dtu', 'bmvs'])
-def test_train_gradients_vs_fp64_oracle(kind):
+def test_train_gradients_vs_fp64_oracle(kind, engine):
     """All parameter gradients of one train step against fp64 autograd on the oracle, same sample positions."""
     R = 48
-    model = build_model(kind, perturb=True, beta=0.05, device=DEV).train()
+    model = build_model(kind, perturb=True, beta=0.05, device=DEV).train().set_engine(engine)
     sd = state_dict_cpu(model)
     inp = S.make_input(kind, R)
     torch.manual_seed(321)
@@ -206,7 +214,7 @@ def test_train_gradients_vs_fp64_oracle(kind):
         e = rel_err(og.cpu(), rg) if float(rg.norm()) > 1e-10 else float(og.norm())
         rows.append((e, name, float(rg.norm())))
     rows.sort(reverse=True)
-    assert rows[0][0] < 5e-3, rows[:6]
+    assert rows[0][0] < (5e-3 if engine == L.ENGINE_FP32 else 1e-2), rows[:6]
 
 
 def test_state_dict_roundtrip_and_optimizer_step():

@@ -1,0 +1,155 @@
+"""SVS_ENGINE_TC_SPLIT — the benchmarked tcgen05 engine (split fp16 hi + lo operands in every forward chain, single fp16
+operands in the backward chains) — against the fp64 oracle at the north_star tolerances: rgb / depth max-abs <= 1e-3,
+parameter gradients relative error <= 1e-2.  Sizes: the bench's own (1024 rays = 800 tiles > 148 persistent CTAs, every
+chain — forward, reverse sweep, tangent sweep, backward, weight gradients — walks 5-6 tiles per CTA) and trained-like
+beta (0.01, 0.001), where a 1e-3 sdf error would be 1 beta.  End-to-end tests against the reference's goldens (own
+sampler, no injected sample positions) are in test_gpu_model.py, parametrised over this engine."""
+import pytest
+import torch
+
+from helpers import build_model, conf_of, max_abs, rel_err, state_dict_cpu
+from oracle import volsdf_oracle as O
+import svolsdf_b200._lib as L
+import svolsdf_b200.scene as S
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _points(P, seed=0, radius=3.6):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(P, 3, generator=g)
+    return x / x.norm(dim=1, keepdim=True) * (torch.rand(P, 1, generator=g) * radius)
+
+
+@pytest.mark.parametrize('P', [1, 127, 129, 5000, 131072])
+def test_sdf_forward_vs_fp64_oracle(P):
+    """get_sdf_vals / forward / get_outputs on the split engine vs the fp64 oracle; 131072 points = 1024 tiles (the
+    sampler launch of a 1024-ray step), both sphere-clamp branches (points reach |x| = 3.6 > 3)"""
+    m = build_model('dtu', perturb=True, beta=0.05, device=DEV).set_engine(L.ENGINE_TC_SPLIT)
+    sd = {k: v.double() for k, v in state_dict_cpu(m).items()}
+    x = _points(P, seed=P)
+    with torch.no_grad():
+        y_ref = O.sdf_net(sd, 'implicit_network', x.double(), 6)
+        s_ref = O.sphere_clamp(y_ref[:, :1], x.double(), 3.0, float(conf_of('dtu').get_config('implicit_network').get('sphere_scale', 1.0)))
+        xd = x.to(DEV)
+        s = m.implicit_network.get_sdf_vals(xd).cpu()
+        y = m.implicit_network(xd).cpu()
+        s2, f2, g2 = m.implicit_network.get_outputs(xd)
+    # |sdf| reaches ~15 in the clamp region: 5e-5 absolute is 3e-6 relative there
+    assert max_abs(s, s_ref) < 5e-5, max_abs(s, s_ref)
+    assert max_abs(y, y_ref) < 5e-5, max_abs(y, y_ref)
+    assert max_abs(s2.cpu(), s_ref) < 5e-5 and max_abs(f2.cpu(), y_ref[:, 1:]) < 5e-5
+    if P <= 5000:
+        xg = x.double().requires_grad_(True)
+        yy = O.sphere_clamp(O.sdf_net(sd, 'implicit_network', xg, 6)[:, :1], xg, 3.0,
+                            float(conf_of('dtu').get_config('implicit_network').get('sphere_scale', 1.0)))
+        g_ref = torch.autograd.grad(yy.sum(), xg)[0]
+        # the reverse sweep keeps single fp16 operands: normals to ~1e-3 relative
+        assert rel_err(g2.cpu(), g_ref) < 2e-3, rel_err(g2.cpu(), g_ref)
+
+
+@pytest.mark.parametrize('engine', [pytest.param(L.ENGINE_TC_SPLIT, id='tc_split'), pytest.param(L.ENGINE_FP32, id='fp32')])
+@pytest.mark.parametrize('beta', [0.05, 0.01, 0.001])
+def test_train_step_1024_rays_vs_fp64_oracle(beta, engine):
+    """The bench's step (1024 rays, L1 + 0.1 eikonal) on the bench's engine: outputs and ALL parameter gradients against
+    fp64 autograd on the oracle, on the sample positions the model drew with its own sampler."""
+    R = 1024
+    model = build_model('dtu', perturb=True, beta=beta, device=DEV).train().set_engine(engine)
+    sd = state_dict_cpu(model)
+    inp = S.make_input('dtu', R)
+    gt = S.gt_rgb(R)
+    torch.manual_seed(321)
+    out = model({k: v.to(DEV) for k, v in inp.items()}, fast=1)
+    loss = (out['rgb_values'] - gt.reshape(-1, 3).to(DEV)).abs().mean() + \
+        0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+    model.zero_grad()
+    loss.backward()
+    ref = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    z, z_eik = model.last_z
+    torch.manual_seed(321)
+    rng = O.draw_rng(R, True)
+    o = O.volsdf_forward(ref, conf_of('dtu'), inp, True, fast=1, rng=rng, dtype=torch.float64,
+                         z_override=(z.cpu(), z_eik.cpu(), None))
+    rl = O.volsdf_loss(o, gt)
+    rl.backward()
+    errs = {k: max_abs(out[k].detach().cpu(), o[k].detach()) for k in ('rgb_values', 'depth_values', 'weights', 'grad_theta')}
+    rows = []
+    for name, p in model.named_parameters():
+        rg = ref[name].grad
+        if rg is None or float(rg.norm()) < 1e-10:
+            continue
+        rows.append((rel_err(p.grad.cpu(), rg), name))
+    rows.sort(reverse=True)
+    print('beta %g: %s | loss %.7f vs %.7f | worst grads %s' % (beta, errs, float(loss), float(rl), rows[:4]))
+    assert errs['rgb_values'] < 1e-3 and errs['depth_values'] < 1e-3, errs
+    assert errs['grad_theta'] < 5e-3 and errs['weights'] < 1e-3, errs      # normals: single-fp16 reverse sweep
+    assert abs(float(loss) - float(rl)) < 1e-4
+    assert len(rows) == 43 and rows[0][0] < 1e-2, rows[:6]
+
+
+def test_bmvs_train_step_vs_fp64_oracle():
+    """BlendedMVS model (background SDF net with d_in = 4 / 10 frequencies, 'nerf' rendering net), 256 rays"""
+    R = 256
+    model = build_model('bmvs', perturb=True, beta=0.02, device=DEV).train().set_engine(L.ENGINE_TC_SPLIT)
+    sd = state_dict_cpu(model)
+    inp = S.make_input('bmvs', R)
+    gt = S.gt_rgb(R)
+    torch.manual_seed(321)
+    out = model({k: v.to(DEV) for k, v in inp.items()}, fast=1)
+    loss = (out['rgb_values'] - gt.reshape(-1, 3).to(DEV)).abs().mean() + \
+        0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+    model.zero_grad()
+    loss.backward()
+    ref = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+    z, z_eik = model.last_z
+    torch.manual_seed(321)
+    rng = O.draw_rng(R, True, bg=True)
+    o = O.volsdf_bg_forward(ref, conf_of('bmvs'), inp, True, fast=1, rng=rng, dtype=torch.float64,
+                            z_override=((z[0].cpu(), z[1].cpu()), z_eik.cpu(), None))
+    rl = O.volsdf_loss(o, gt)
+    rl.backward()
+    assert max_abs(out['rgb_values'].detach().cpu(), o['rgb_values'].detach()) < 1e-3
+    assert max_abs(out['weights'].detach().cpu(), o['weights'].detach()) < 1e-3
+    # depth = sum(w z) / (sum(w) + 1e-8) is ill-conditioned on rays that hit nothing (the BlendedMVS model has no sphere
+    # clamp; same convention as test_gpu_model.py); depth_values_all inherits that through 1 / depth of the background
+    hit = o['weights'].detach().sum(1, keepdim=True) > 1e-2
+    assert max_abs(out['depth_values'].detach().cpu()[hit], o['depth_values'].detach()[hit]) < 1e-3
+    rows = []
+    for name, p in model.named_parameters():
+        rg = ref[name].grad
+        if rg is None or float(rg.norm()) < 1e-10:
+            continue
+        rows.append((rel_err(p.grad.cpu(), rg), name))
+    rows.sort(reverse=True)
+    print('bmvs worst grads', rows[:4])
+    assert rows[0][0] < 1e-2, rows[:6]
+
+
+def test_eval_render_matches_fp32_engine():
+    """eval forward at beta = 0.01 (5 sampler iterations, 700 rays = 5 x 700 x 128 sampler points).  Both engines run
+    their own sampler (same iteration count required); the maps are compared on the fp32 engine's sample positions:
+    with 700 rays some graze the surface, where 1e-6 of sdf moves a bisection decision and with it the samples — the
+    end-to-end (own positions) comparison against the reference's recorded outputs is test_gpu_model.py's golden test."""
+    a = build_model('dtu', perturb=True, beta=0.01, device=DEV).eval()
+    b = build_model('dtu', perturb=True, beta=0.01, device=DEV).eval().set_engine(L.ENGINE_TC_SPLIT)
+    inp = {k: v.to(DEV) for k, v in S.make_input('dtu', 700).items()}
+    torch.manual_seed(5)
+    oa = a(inp)
+    zs = a.last_z
+    torch.manual_seed(5)
+    ob_own = b(inp)
+    assert a.ray_sampler.last_iters == b.ray_sampler.last_iters == 5
+    d = (ob_own['depth_values'] - oa['depth_values']).abs().flatten()
+    assert float(d.kthvalue(int(0.98 * d.numel()))[0]) < 1e-3 and max_abs(ob_own['rgb_values'], oa['rgb_values']) < 1e-3
+    orig = b.ray_sampler.get_z_vals
+
+    def patched(*args, **kw):
+        orig(*args, **kw)
+        return zs
+    b.ray_sampler.get_z_vals = patched
+    torch.manual_seed(5)
+    ob = b(inp)
+    assert max_abs(ob['rgb_values'], oa['rgb_values']) < 1e-3
+    assert max_abs(ob['depth_values'], oa['depth_values']) < 1e-3
+    assert max_abs(ob['normal_map'], oa['normal_map']) < 5e-3
