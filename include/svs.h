@@ -26,7 +26,7 @@ extern "C" {
 
 #define SVS_MAX_LAYERS 12
 #define SVS_OPT_MAX_TENSORS 96
-#define SVS_ABI_VERSION 4
+#define SVS_ABI_VERSION 5
 
 typedef enum {
   SVS_OK = 0,

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             load(st.w_lo + (size_t)kb * bytes, bytes);
             load(st.w + (size_t)kb * bytes, bytes);
           }
-          for (int kb = 0; kb < st.KB; ++kb) load(st.w + (size_t)kb * bytes, bytes);
+          // main term, last block first: W_hi(KB-1) is still in its slot from the cross term
+          for (int kb = st.KB - 2; kb >= 0; --kb) load(st.w + (size_t)kb * bytes, bytes);
         }
       }
     }
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               }
               umma_commit(&bars->w_empty[slot]);
             }
-            {   // A_lo(kb) x W_hi(kb)
+            {   // A_lo(kb) x W_hi(kb); the last block stays for the first main-term block
               const int slot = seq % NS;
               const uint32_t use = seq / NS;
               ++seq;
@@ -201,10 +202,15 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 umma_f16(acc, make_smem_desc(al + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+              if (kb == st.KB - 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  umma_f16(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+              }
               umma_commit(&bars->w_empty[slot]);
             }
           }
-          for (int kb = 0; kb < st.KB; ++kb) {   // main term A_hi(kb) x W_hi(kb)
+          for (int kb = st.KB - 2; kb >= 0; --kb) {   // main term A_hi(kb) x W_hi(kb), remaining blocks
             const int slot = seq % NS;
             const uint32_t use = seq / NS;
             ++seq;

