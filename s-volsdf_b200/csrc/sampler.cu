@@ -256,6 +256,224 @@ sampler_bound_kernel(svs_sampler_cfg c, int64_t R, int n, int n_new, const float
   if (lane == 0 && any_nc) atomicOr(not_converged, 1);
 }
 
+
+// ----------------------------------------------------------------------------------------------------
+// bound, lane-contiguous layout (n <= 1024).  Lane L owns the C consecutive samples C L .. C L + C - 1, so a prefix sum
+// over the row is a serial prefix inside the lane plus ONE 5-step warp scan of the lane totals (the segment layout above
+// runs n / 32 dependent scans per quantity and evaluation: 56 shuffles at n = 128, here 17).  Rows sit in shared memory
+// at index (i / C) * (C + 1) + i % C (odd stride: conflict-free for the even C used); for C <= 8 the pre-scaled row is
+// held in registers over the 11 evaluations.  The canonical fp64 evaluation (only inside the decision band) reads the
+// same rows in the original segment order, so the beta sequence stays bit-identical to the oracle's.
+// ----------------------------------------------------------------------------------------------------
+constexpr int kBoundWarps = 8;
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int C>
+__device__ __forceinline__ int pidx(int i) { return (i / C) * (C + 1) + (i % C); }
+
+template <int C>
+__device__ __forceinline__ float error_bound_padded(const float* sS, const float* sD, const float* sX, int n, float beta, int lane) {
+  double carry_i = 0, carry_e = 0;
+  float best = -CUDART_INF_F;
+  const float four_b2 = 4.0f * (beta * beta);
+  for (int base = 0; base < n - 1; base += 32) {
+    int i = base + lane;
+    float sfe = 0.f, es = 0.f;
+    bool valid = i < n - 1;
+    if (valid) {
+      float d = sD[pidx<C>(i)];
+      sfe = d * laplace<true>(sS[pidx<C>(i)], beta);
+      es = (t_exp<true>(-sX[pidx<C>(i)] / beta) * (d * d)) / four_b2;
+    }
+    double incl_i = warp_incl_scan<double>((double)sfe, lane);
+    double incl_e = warp_incl_scan<double>((double)es, lane);
+    float integral = (float)(carry_i + excl_of(incl_i, lane));
+    float eint = (float)(carry_e + incl_e);
+    if (valid) {
+      float bo = (fminf(t_exp<true>(eint), 1.0e6f) - 1.0f) * t_exp<true>(-integral);
+      best = fmaxf(best, bo);
+    }
+    carry_i += __shfl_sync(0xffffffffu, incl_i, 31);
+    carry_e += __shfl_sync(0xffffffffu, incl_e, 31);
+  }
+  return warp_max(best);
+}
+
+// pre-scaled row of one lane: a = -log2e |s|, hs = sgn(s) / 2, d = dist, dq = dist^2 / 4, x = -log2e d*
+template <int C>
+struct LaneRow {
+  float a[C], hs[C], d[C], dq[C], x[C];
+};
+template <int C>
+__device__ __forceinline__ void lane_row_load(LaneRow<C>& r, const float* sS, const float* sD, const float* sX, int lane) {
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const int o = lane * (C + 1) + j;
+    const float sv = sS[o], d = sD[o];
+    r.a[j] = -kLog2e * fabsf(sv);
+    r.hs[j] = 0.5f * sgn(sv);
+    r.d[j] = d;
+    r.dq[j] = 0.25f * (d * d);
+    r.x[j] = -kLog2e * sX[o];
+  }
+}
+
+// (min(exp(E_i), 1e6) - 1) exp(-I_i) maximised over the row, plain fp32 + MUFU: decides `bound <= eps` outside the band
+template <int C, bool REG>
+__device__ __forceinline__ float error_bound_lanes(const LaneRow<C>& row, const float* sS, const float* sD, const float* sX,
+                                                   float beta, int lane) {
+  const float inv_b = 1.0f / beta, q = inv_b * inv_b;
+  float Fi[C], Gi[C];
+  float F = 0.f, G = 0.f;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    float a, hs, d, dq, x;
+    if (REG) {
+      a = row.a[j]; hs = row.hs[j]; d = row.d[j]; dq = row.dq[j]; x = row.x[j];
+    } else {
+      const int o = lane * (C + 1) + j;
+      const float sv = sS[o];
+      d = sD[o];
+      a = -kLog2e * fabsf(sv);
+      hs = 0.5f * sgn(sv);
+      dq = 0.25f * (d * d);
+      x = -kLog2e * sX[o];
+    }
+    const float e = ex2f(a * inv_b);                          // exp(-|s| / beta)
+    const float sig = inv_b * fmaf(hs, e - 1.0f, 0.5f);       // Laplace CDF density
+    F = fmaf(d, sig, F);
+    Fi[j] = F;
+    G = fmaf(ex2f(x * inv_b) * dq, q, G);
+    Gi[j] = G;
+  }
+  float incF = F, incG = G;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float tf = __shfl_up_sync(0xffffffffu, incF, o), tg = __shfl_up_sync(0xffffffffu, incG, o);
+    if (lane >= o) { incF += tf; incG += tg; }
+  }
+  float baseF = __shfl_up_sync(0xffffffffu, incF, 1), baseG = __shfl_up_sync(0xffffffffu, incG, 1);
+  if (lane == 0) { baseF = 0.f; baseG = 0.f; }
+  // intervals beyond n - 2 carry dist = 0: they repeat the last valid prefix with a larger integral and never win the max
+  float best = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    const float I = baseF + (j ? Fi[j - 1] : 0.f), E = baseG + Gi[j];
+    best = fmaxf(best, (fminf(ex2f(E * kLog2e), 1.0e6f) - 1.0f) * ex2f(-I * kLog2e));
+  }
+  return warp_max(best);
+}
+
+template <bool X, int C>
+__global__ void __launch_bounds__(kBoundWarps * 32)
+sampler_bound_lanes_kernel(svs_sampler_cfg c, int64_t R, int n, int n_new, const float* __restrict__ z,
+                           const float* __restrict__ sdf_old, const float* __restrict__ sdf_new,
+                           const int32_t* __restrict__ samples_idx, float* __restrict__ sdf_out,
+                           const float* __restrict__ beta_param, float beta_min, float* __restrict__ beta,
+                           int32_t* __restrict__ not_converged) {
+  constexpr int ROW = 32 * (C + 1);
+  constexpr bool REG = C <= 8;
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sS = smem + warp * (4 * ROW);
+  float* sZ = sS + ROW;
+  float* sD = sZ + ROW;
+  float* sX = sD + ROW;
+  const float beta0 = fabsf(__ldg(beta_param)) + beta_min;
+  const int n_old = n - n_new;
+  bool any_nc = false;
+  for (int64_t ray = blockIdx.x * (int64_t)kBoundWarps + warp; ray < R; ray += (int64_t)gridDim.x * kBoundWarps) {
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const int i = lane + 32 * k;
+      float s = 0.f, zz = 0.f;
+      if (i < n) {
+        if (samples_idx) {
+          int src = samples_idx[ray * n + i];
+          s = (src < n_old) ? sdf_old[ray * n_old + src] : sdf_new[ray * n_new + (src - n_old)];
+        } else {
+          s = sdf_new[ray * n_new + i];
+        }
+        sdf_out[ray * n + i] = s;
+        zz = z[ray * n + i];
+      }
+      sS[pidx<C>(i)] = s;
+      sZ[pidx<C>(i)] = zz;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < C; ++k) {
+      const int i = lane + 32 * k;
+      float d = 0.f, ds = 0.f;
+      if (i < n - 1) {
+        d = sZ[pidx<C>(i + 1)] - sZ[pidx<C>(i)];
+        ds = d_star_of(d, sS[pidx<C>(i)], sS[pidx<C>(i + 1)]);
+      }
+      sD[pidx<C>(i)] = d;
+      sX[pidx<C>(i)] = ds;
+    }
+    __syncwarp();
+    LaneRow<REG ? C : 1> row;
+    if (REG) lane_row_load<REG ? C : 1>(row, sS, sD, sX, lane);
+    auto decide = [&](float bt) -> float {
+      float ef;
+      if constexpr (REG) ef = error_bound_lanes<C, true>(row, sS, sD, sX, bt, lane);
+      else ef = error_bound_lanes<C, false>(LaneRow<C>(), sS, sD, sX, bt, lane);
+      if (!X || fabsf(ef - c.eps) > kBoundBand * c.eps) return ef;   // NaN: falls through to the canonical evaluation
+      return error_bound_padded<C>(sS, sD, sX, n, bt, lane);
+    };
+    float b = beta[ray];
+    float err = decide(beta0);
+    if (err <= c.eps) b = beta0;
+    float bmin = beta0, bmax = b;
+    if (bmin != bmax) {   // bmin == bmax: every midpoint is beta0 again and the outcome is known
+      for (int j = 0; j < c.beta_iters; ++j) {
+        float mid = (bmin + bmax) / 2.0f;
+        err = decide(mid);
+        if (err <= c.eps) bmax = mid;
+        if (err > c.eps) bmin = mid;
+      }
+    }
+    if (lane == 0) beta[ray] = bmax;
+    any_nc |= (bmax > beta0);
+    __syncwarp();
+  }
+  if (lane == 0 && any_nc) atomicOr(not_converged, 1);
+}
+
+template <bool X, int C>
+static int launch_bound_lanes(const svs_sampler_cfg* c, int64_t R, int n, int n_new, const float* z, const float* sdf_old,
+                              const float* sdf_new, const int32_t* samples_idx, float* sdf, const float* beta_param,
+                              float beta_min, float* beta, int32_t* not_converged, cudaStream_t st) {
+  size_t smem = (size_t)kBoundWarps * 4 * 32 * (C + 1) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    SVS_CUDA_OK(cudaFuncSetAttribute(sampler_bound_lanes_kernel<X, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int64_t blocks = cdiv(R, kBoundWarps);
+  int64_t cap = (int64_t)kNumSMs * (C <= 8 ? 6 : 2);
+  sampler_bound_lanes_kernel<X, C><<<(int)(blocks < cap ? blocks : cap), kBoundWarps * 32, smem, st>>>(
+      *c, R, n, n_new, z, sdf_old, sdf_new, samples_idx, sdf, beta_param, beta_min, beta, not_converged);
+  return SVS_OK;
+}
+template <bool X>
+static int launch_bound_lanes_x(int C, const svs_sampler_cfg* c, int64_t R, int n, int n_new, const float* z, const float* sdf_old,
+                                const float* sdf_new, const int32_t* samples_idx, float* sdf, const float* beta_param,
+                                float beta_min, float* beta, int32_t* not_converged, cudaStream_t st) {
+#define SVS_BOUND_CASE(CC) \
+  if (C <= CC) return launch_bound_lanes<X, CC>(c, R, n, n_new, z, sdf_old, sdf_new, samples_idx, sdf, beta_param, beta_min, beta, not_converged, st)
+  SVS_BOUND_CASE(4);
+  SVS_BOUND_CASE(8);
+  SVS_BOUND_CASE(12);
+  SVS_BOUND_CASE(16);
+  SVS_BOUND_CASE(20);
+  SVS_BOUND_CASE(24);
+  SVS_BOUND_CASE(32);
+#undef SVS_BOUND_CASE
+  return SVS_ERR_INVALID;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // resample: weights/transmittance, pdf, cdf, inverse CDF, stable merge (ray_sampler.py:126-190)
 // ----------------------------------------------------------------------------------------------------
@@ -451,6 +669,73 @@ sampler_finalize_kernel(svs_sampler_cfg c, int64_t R, int n, int n_samples, int 
   }
 }
 
+
+// finalize with the row in registers (m_pad = 32 C <= 256): C keys per lane, key e = C lane + r.  The reference discards
+// the sort indices (ray_sampler.py:208), so plain min / max compare-exchanges sort the values; partners at distance < C
+// are in the same lane, the others one shuffle away.  (The shared-memory bitonic sort above spent 0.94 ms on 262144 rays,
+// a third of the whole sampler iteration.)
+template <int C>
+__global__ void __launch_bounds__(kSampWarps * 32)
+sampler_finalize_regs_kernel(svs_sampler_cfg c, int64_t R, int n, int n_samples, const float* __restrict__ z,
+                             const float* __restrict__ samples, const int32_t* __restrict__ extra_idx, int n_extra,
+                             const float* __restrict__ far_ray, const int64_t* __restrict__ eik_idx,
+                             float* __restrict__ z_final, float* __restrict__ z_eik) {
+  constexpr int M = 32 * C;
+  __shared__ float srow[kSampWarps][M + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = n_samples + 2 + n_extra;
+  for (int64_t ray = blockIdx.x * (int64_t)kSampWarps + warp; ray < R; ray += (int64_t)gridDim.x * kSampWarps) {
+    const float far = (c.far < 0.f) ? far_ray[ray] : c.far;
+    // coalesced gather into shared memory, then C consecutive keys per lane
+    for (int i = lane; i < M; i += 32) {
+      float v = CUDART_INF_F;
+      if (i < n_samples) v = samples[ray * n_samples + i];
+      else if (i == n_samples) v = c.near;
+      else if (i == n_samples + 1) v = far;
+      else if (i < m) v = z[ray * n + extra_idx[i - n_samples - 2]];
+      srow[warp][i] = v;
+    }
+    __syncwarp();
+    float v[C];
+#pragma unroll
+    for (int r = 0; r < C; ++r) v[r] = srow[warp][lane * C + r];
+#pragma unroll
+    for (int k = 2; k <= M; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= C) {
+          const int lj = j / C;                       // partner lane distance
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            const int e = lane * C + r;
+            const float p = __shfl_xor_sync(0xffffffffu, v[r], lj);
+            const bool up = (e & k) == 0, low = (e & j) == 0;   // low element of an ascending pair keeps the minimum
+            v[r] = (up == low) ? fminf(v[r], p) : fmaxf(v[r], p);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            if ((r & j) == 0) {
+              const int e = lane * C + r;
+              const bool up = (e & k) == 0;
+              const float a = v[r], b = v[r | j];
+              v[r] = up ? fminf(a, b) : fmaxf(a, b);
+              v[r | j] = up ? fmaxf(a, b) : fminf(a, b);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < C; ++r) srow[warp][lane * C + r] = v[r];
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) z_final[ray * m + i] = srow[warp][i];
+    if (lane == 0 && z_eik) z_eik[ray] = srow[warp][(int)eik_idx[ray]];
+    __syncwarp();
+  }
+}
+
 static int samp_grid(int64_t R) {
   int64_t blocks = cdiv(R, kSampWarps);
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -501,6 +786,15 @@ extern "C" int svs_sampler_bound(const svs_sampler_cfg* c, int64_t R, int32_t n,
   size_t smem = (size_t)kSampWarps * 4 * n * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("sampler_bound", 0.0, (double)R * (4.0 * n * (samples_idx ? 4 : 3) + 8), st);
+  if (n <= 1024) {   // lane-contiguous kernel; the segment kernel below serves longer rows
+    const int C = (n + 31) / 32;
+    if (c->exact)
+      SVS_TRY(launch_bound_lanes_x<true>(C, c, R, n, n_new, z, sdf_old, sdf_new, samples_idx, sdf, beta_param, beta_min, beta, not_converged, st));
+    else
+      SVS_TRY(launch_bound_lanes_x<false>(C, c, R, n, n_new, z, sdf_old, sdf_new, samples_idx, sdf, beta_param, beta_min, beta, not_converged, st));
+    SVS_LAUNCH_OK();
+    return SVS_OK;
+  }
   if (c->exact) {
     SVS_TRY(set_smem(sampler_bound_kernel<true>, smem));
     sampler_bound_kernel<true><<<samp_grid(R), kSampWarps * 32, smem, st>>>(
@@ -554,6 +848,17 @@ extern "C" int svs_sampler_finalize(const svs_sampler_cfg* c, int64_t R, int32_t
   int m_pad = next_pow2(m < 64 ? 64 : m);
   size_t smem = (size_t)kSampWarps * 2 * m_pad * sizeof(float);
   ProfScope ps("sampler_finalize", 0.0, (double)R * (4.0 * (n_samples + n_extra) + 4.0 * m + 16), (cudaStream_t)stream);
+  if (m_pad <= 256) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m_pad == 64)
+      sampler_finalize_regs_kernel<2><<<samp_grid(R), kSampWarps * 32, 0, st>>>(*c, R, n, n_samples, z, samples, extra_idx, n_extra, far_ray, eik_idx, z_final, z_eik);
+    else if (m_pad == 128)
+      sampler_finalize_regs_kernel<4><<<samp_grid(R), kSampWarps * 32, 0, st>>>(*c, R, n, n_samples, z, samples, extra_idx, n_extra, far_ray, eik_idx, z_final, z_eik);
+    else
+      sampler_finalize_regs_kernel<8><<<samp_grid(R), kSampWarps * 32, 0, st>>>(*c, R, n, n_samples, z, samples, extra_idx, n_extra, far_ray, eik_idx, z_final, z_eik);
+    SVS_LAUNCH_OK();
+    return SVS_OK;
+  }
   sampler_finalize_kernel<<<samp_grid(R), kSampWarps * 32, smem, (cudaStream_t)stream>>>(
       *c, R, n, n_samples, m_pad, z, samples, extra_idx, n_extra, far_ray, eik_idx, z_final, z_eik);
   SVS_LAUNCH_OK();

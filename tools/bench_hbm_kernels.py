@@ -67,7 +67,17 @@ for exact in (1, 0):
     n = 128
     t_rand = torch.rand(R, n, generator=g).to(dev)
     zz = torch.empty(R, n, device=dev); bb = torch.empty(R, device=dev)
-    sdf_new = ((torch.rand(R, n, generator=g) - 0.3) * 0.5).to(dev)
+    # sdf rows of the synthetic DTU scene: unit sphere of radius 0.6 seen from (0, 0, -2.5) through the DTU
+    # pinhole, with the bounding-sphere clamp min(sdf, 20 (3 - |x|)) of the benchmark model; samples = sampler_init's z
+    import svolsdf_b200.scene as SC
+    from svolsdf_b200 import functional as FF
+    inp = SC.make_input('dtu', R, pixels='perm')
+    dirs, cam, _ = FF.raygen(inp['uv'][0].to(dev), inp['pose'][0].to(dev), inp['intrinsics'][0].to(dev))
+    L.call('svs_sampler_init', cfg, R, n, lin.data_ptr() if False else _linspace(n, dev).data_ptr(), t_rand.data_ptr(), None, zz.data_ptr(), bb.data_ptr(), L.stream())
+    pts = cam[:, None, :] + zz[:, :, None] * dirs[:, None, :]
+    nr = pts.norm(dim=-1)
+    sdf_new = torch.minimum(nr - 0.6, 20.0 * (3.0 - nr)).contiguous()
+    del pts, nr
     sdf_m = torch.empty(R, n, device=dev); flag = torch.zeros(1, dtype=torch.int32, device=dev)
     u = torch.rand(R, 64, generator=g).to(dev); samples = torch.empty(R, 64, device=dev)
     extra = torch.randperm(n)[:32].to(torch.int32).to(dev); eik = torch.randint(98, (R,)).to(dev)
@@ -85,6 +95,13 @@ for exact in (1, 0):
                eik.data_ptr(), zf.data_ptr(), ze.data_ptr(), st)
     ms = timeit(it)
     res.append(('sampler_train_iteration_%s' % ('exact_fp64' if exact else 'fast_fp32'), 2212.0, ms))
+    L.prof_enable(True)
+    for _ in range(5):
+        it()
+    torch.cuda.synchronize()
+    pr = L.prof_collect()
+    L.prof_enable(False)
+    print(json.dumps({'sampler_breakdown_ms_per_launch': {k: v['ms'] / v['launches'] for k, v in pr.items()}, 'exact': exact}))
 
 # MVS cost lookup (VolOpt.cost_mapping): 3 source views of 48 x 288 x 384 (the paper configuration, vsdf.py:369), 98
 # samples per ray.  Bytes per ray: 98 samples x (12 in + 9 out + 3 views x 16 taps x 4 B gathered from L2-resident volumes)
