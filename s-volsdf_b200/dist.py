@@ -12,8 +12,14 @@ import torch.distributed as dist
 from .model.ray_sampler import RefRng
 
 
-def shard_range(n, rank, world):
-    """Contiguous [lo, hi) of `n` items for `rank`; the first n % world ranks get one extra item."""
+def shard_range(n, rank, world, align=1):
+    """Contiguous [lo, hi) of `n` items for `rank`; the first ranks get the extra items.  `align` > 1 shards whole blocks
+    of `align` items (rendering: convergence groups of 512 rays must not straddle ranks, or the sharded frame would group
+    rays differently from the unsharded one)."""
+    if align > 1:
+        nb = (n + align - 1) // align
+        lo_b, hi_b = shard_range(nb, rank, world)
+        return min(lo_b * align, n), min(hi_b * align, n)
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)

@@ -185,6 +185,12 @@ class ErrorBoundSampler(RaySampler):
         self.exact = True          # fp64 transcendentals + fp64 scans (bit-exact vs the oracle)
         self.trace = None          # set to a list to record per-iteration tensors (tests)
         self.last_iters = 0
+        # eval only: rays [k * group_size, (k + 1) * group_size) of ONE call form a convergence group of their own, i.e.
+        # the call computes what the reference computes when its render loop feeds the model `split_n_pixels` rays at a
+        # time (vsdf.py:246-262, utils/general.py:24-39; 500 at train-time renders, 512 in eval_vsdf.py).  None: the whole
+        # call is one group (the reference's semantics for a single model call).
+        self.group_size = None
+        self.last_group_iters = None
 
     def get_z_vals(self, ray_dirs, cam_loc, model, fast=-1, iter_step=None, _rng=None, _sdf_fn=None):
         R = ray_dirs.shape[0]
@@ -204,6 +210,11 @@ class ErrorBoundSampler(RaySampler):
             far_ray = rend_util.get_sphere_intersections(cam_loc, ray_dirs, r=self.scene_bounding_sphere)[:, 1].contiguous()
         cfg = _cfg(self.near, -1.0 if self.inverse_sphere_bg else self.far, self.eps, self.add_tiny,
                    self.beta_iters, self.exact)
+
+        if (self.group_size and not training and R > self.group_size and self.trace is None and max_total_iters > 0):
+            return self._get_z_vals_grouped(ray_dirs, cam_loc, model, rng, sdf_fn, far_ray, cfg, int(self.group_size),
+                                            max_total_iters, beta_param, beta_min, iter_step)
+        self.last_group_iters = None
 
         # uniform start + Lemma-2 beta (ray_sampler.py:72-78)
         z, beta = self.uniform_sampler.get_z_vals(ray_dirs, cam_loc, model, iter_step=iter_step, _rng=rng,
@@ -262,3 +273,96 @@ class ErrorBoundSampler(RaySampler):
             z_bg = z_bg * (1. / self.scene_bounding_sphere)
             return (z_final, z_bg), z_eik
         return z_final, z_eik
+
+
+def _grouped(self, ray_dirs, cam_loc, model, rng, sdf_fn, far_ray, cfg, G, max_total_iters, beta_param, beta_min, iter_step):
+    """Eval sampling of R rays as ceil(R / G) independent convergence groups inside one call: every
+    group runs the reference's loop (ray_sampler.py:83-190) until ITS rays have converged (`beta_ray.max() > beta0` is
+    taken per group, :136); groups that stop are finalised and leave the working set, the others get 128 more samples.
+    All active groups share the sample count (128 per iteration), so one launch per kernel serves them all.  One host
+    synchronisation per iteration (the reference has one per group and iteration)."""
+    R = ray_dirs.shape[0]
+    dev = ray_dirs.device
+    st = L.stream()
+    n_extra = self.N_samples_extra
+    m = self.N_samples + 2 + n_extra
+    z_final = torch.empty(R, m, dtype=torch.float32, device=dev)
+    z_eik = torch.empty(R, 1, dtype=torch.float32, device=dev)
+    eik_idx = rng.randint(m, (R,))
+    z, beta = self.uniform_sampler.get_z_vals(ray_dirs, cam_loc, model, iter_step=iter_step, _rng=rng,
+                                              _far_ray=far_ray, _want_beta=True)
+    n_groups = (R + G - 1) // G
+    idx = torch.arange(R, device=dev)
+    gid = torch.div(idx, G, rounding_mode='floor')
+    beta0 = beta_param.abs() + beta_min
+    dirs, cams, far = ray_dirs, cam_loc, far_ray
+    samples, samples_idx, sdf = z, None, None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    group_iters = [0] * n_groups
+    it = 0
+    while True:
+        Ra, n, n_new = z.shape[0], z.shape[1], samples.shape[1]
+        pts = F.ray_points(cams, dirs, samples).reshape(-1, 3)
+        with torch.no_grad():
+            sdf_new = sdf_fn(pts).reshape(Ra, n_new).contiguous()
+        sdf_m = torch.empty(Ra, n, dtype=torch.float32, device=dev)
+        L.call('svs_sampler_bound', cfg, Ra, n, n_new, ptr(z), ptr(sdf), ptr(sdf_new), ptr(samples_idx), ptr(sdf_m),
+               ptr(beta_param), beta_min, ptr(beta), ptr(flag), st)
+        sdf = sdf_m
+        it += 1
+        if it < max_total_iters:
+            nc_group = torch.zeros(n_groups, dtype=torch.int32, device=dev)
+            nc_group.index_add_(0, gid, (beta > beta0).to(torch.int32))
+            cont_row = nc_group[gid] > 0
+            sel_c = cont_row.nonzero().squeeze(1)          # host sync: how many rays go on
+            n_cont = int(sel_c.numel())
+        else:
+            cont_row, sel_c, n_cont = None, None, 0
+        if n_cont < Ra:
+            if n_cont == 0:
+                zf, sf, bf, idx_f, far_f, gid_f = z, sdf, beta, idx, far, gid
+            else:
+                sel_f = (~cont_row).nonzero().squeeze(1)
+                zf, sf, bf, idx_f, gid_f = z[sel_f].contiguous(), sdf[sel_f].contiguous(), beta[sel_f].contiguous(), idx[sel_f], gid[sel_f]
+                far_f = far[sel_f].contiguous() if far is not None else None
+            Rf = zf.shape[0]
+            n_u = self.N_samples
+            smp = torch.empty(Rf, n_u, dtype=torch.float32, device=dev)
+            L.call('svs_sampler_resample', cfg, Rf, n, n_u, 0, ptr(zf), ptr(sf), ptr(bf), ptr(_linspace(n_u, dev)), 0,
+                   ptr(smp), None, None, None, st)
+            extra_idx = _extra_idx_eval(n, n_extra, dev) if n_extra > 0 else None
+            zfin = torch.empty(Rf, m, dtype=torch.float32, device=dev)
+            zeik = torch.empty(Rf, 1, dtype=torch.float32, device=dev)
+            L.call('svs_sampler_finalize', cfg, Rf, n, n_u, ptr(zf), ptr(smp), ptr(extra_idx), n_extra, ptr(far_f),
+                   ptr(eik_idx[idx_f].contiguous()), ptr(zfin), ptr(zeik), st)
+            if n_cont == 0 and Rf == R:
+                z_final, z_eik = zfin, zeik
+            else:
+                z_final.index_copy_(0, idx_f, zfin)
+                z_eik.index_copy_(0, idx_f, zeik)
+            for g in torch.unique(gid_f).tolist():
+                group_iters[g] = it
+        if n_cont == 0:
+            break
+        if n_cont < Ra:
+            z, sdf, beta = z[sel_c].contiguous(), sdf[sel_c].contiguous(), beta[sel_c].contiguous()
+            dirs, cams, idx, gid = dirs[sel_c].contiguous(), cams[sel_c].contiguous(), idx[sel_c], gid[sel_c]
+            far = far[sel_c].contiguous() if far is not None else None
+        Rc = z.shape[0]
+        n_u = self.N_samples_eval
+        samples = torch.empty(Rc, n_u, dtype=torch.float32, device=dev)
+        z_m = torch.empty(Rc, n + n_u, dtype=torch.float32, device=dev)
+        sidx = torch.empty(Rc, n + n_u, dtype=torch.int32, device=dev)
+        L.call('svs_sampler_resample', cfg, Rc, n, n_u, 1, ptr(z), ptr(sdf), ptr(beta), ptr(_linspace(n_u, dev)), 0,
+               ptr(samples), None, ptr(z_m), ptr(sidx), st)
+        z, samples_idx = z_m, sidx
+    self.last_iters = it
+    self.last_group_iters = group_iters
+    if self.inverse_sphere_bg:
+        z_bg = self.inverse_sphere_sampler.get_z_vals(ray_dirs, cam_loc, model, _rng=rng)
+        z_bg = z_bg * (1. / self.scene_bounding_sphere)
+        return (z_final, z_bg), z_eik
+    return z_final, z_eik
+
+
+ErrorBoundSampler._get_z_vals_grouped = _grouped

@@ -157,3 +157,32 @@ def test_eval_render_matches_fp32_engine():
     assert max_abs(ob['rgb_values'], oa['rgb_values']) < 1e-3
     assert max_abs(ob['depth_values'], oa['depth_values']) < 1e-3
     assert max_abs(ob['normal_map'], oa['normal_map']) < 5e-3
+
+
+@pytest.mark.parametrize('engine', [pytest.param(L.ENGINE_FP32, id='fp32'), pytest.param(L.ENGINE_TC_SPLIT, id='tc_split')])
+def test_grouped_render_equals_the_reference_chunk_loop(engine):
+    """one launch over many rays with 512-ray convergence groups INSIDE it (ErrorBoundSampler.group_size)
+    must equal the reference's render loop, which calls the model on 512 rays at a time (vsdf.py:246-262,
+    eval_vsdf.py:216-228): same sampler iterations per group, same maps ray for ray.  The ray set mixes a group that
+    misses the object (image corner), groups on it, and a ragged tail."""
+    from svolsdf_b200.render import render_rays
+    m = build_model('dtu', perturb=True, beta=0.03, device=DEV).eval().set_engine(engine)
+    inp = S.make_input('dtu', 16)
+    xs = torch.arange(512, dtype=torch.float32)
+    corner = torch.stack([xs % 64, torch.div(xs, 64, rounding_mode='floor')], -1)                    # 64 x 8 block at (0, 0)
+    centre = torch.stack([800 + xs % 32 * 3, 600 + torch.div(xs, 32, rounding_mode='floor') * 3], -1)
+    g = torch.Generator().manual_seed(3)
+    rnd = torch.stack([torch.randint(0, 1600, (812,), generator=g), torch.randint(0, 1200, (812,), generator=g)], -1).float()
+    uv = torch.cat([corner, centre, rnd], 0)[None].to(DEV)                                            # 1836 rays = 3 groups + 300
+    K_, pose = inp['intrinsics'].to(DEV), inp['pose'].to(DEV)
+    torch.manual_seed(3)
+    got = render_rays(m, K_, pose, uv, chunk=4096, group=512)
+    parts, iters = [], []
+    for lo in range(0, uv.shape[1], 512):
+        torch.manual_seed(3)
+        parts.append(m({'intrinsics': K_, 'pose': pose, 'uv': uv[:, lo:lo + 512].contiguous()}))
+        iters.append(m.ray_sampler.last_iters)
+    assert got['sampler_iters'] == iters, (got['sampler_iters'], iters)
+    assert len(set(iters)) > 1, iters          # the groups really stop at different iterations
+    for k in ('rgb_values', 'depth_values', 'normal_map'):
+        assert torch.equal(got[k], torch.cat([p[k] for p in parts], 0)), k

@@ -242,7 +242,7 @@ def test_full_frame_render_helper_matches_chunked_model_calls():
     m = build_model('dtu', perturb=True, beta=0.05, device=DEV).eval().set_engine(L.ENGINE_TC)
     inp = {k: v.to(DEV) for k, v in S.make_input('dtu', 300).items()}
     torch.manual_seed(3)
-    got = render_rays(m, inp['intrinsics'], inp['pose'], inp['uv'], chunk=128)
+    got = render_rays(m, inp['intrinsics'], inp['pose'], inp['uv'], chunk=128, group=None)
     torch.manual_seed(3)
     parts = [m({'intrinsics': inp['intrinsics'], 'pose': inp['pose'], 'uv': inp['uv'][:, lo:lo + 128].contiguous()})
              for lo in range(0, 300, 128)]
