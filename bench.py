@@ -35,14 +35,19 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--rays', type=int, default=1024, help='rays per GPU per step')
-    ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc'])
+    ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc', 'tc_split'],
+                    help='auto = tc_split: the tcgen05 engine that meets the parity contract')
     ap.add_argument('--cpu-rays', type=int, default=128, help='rays per step of the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='train', choices=['train', 'frame'],
-                    help="train: BASELINE configs[1] (default, the headline); frame: configs[2], 1600x1200 full-image render")
+    ap.add_argument('--workload', default='all', choices=['all', 'train', 'frame'],
+                    help="all (default): the headline train step (BASELINE configs[1]) plus `frame` (configs[2]) and `large_batch` "
+                         "(configs[4]) legs in the same JSON line; train / frame: only that one")
+    ap.add_argument('--group', type=int, default=512, help='frame: rays per sampler convergence group (eval_vsdf.py: 512)')
+    ap.add_argument('--large-rays', type=int, default=8192, help='large_batch leg: rays per GPU (8 GPUs: 65536 per step)')
+    ap.add_argument('--ref-rays', type=int, default=None, help='--impl reference: rays per step (default: --rays, the same config)')
+    ap.add_argument('--skip', default='', help='comma list of legs to skip: frame,large,parity,gpu_eager,engines')
     ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
     ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
-    ap.add_argument('--no-parity-leg', action='store_true', help='skip the fp32 parity-engine comparison leg (profiling runs)')
     ap.add_argument('--scene', default='dtu', choices=['dtu', 'bmvs'],
                     help='train workload: dtu = BASELINE configs[1] (the headline); bmvs = configs[3], VolSDFNetworkBG with the '
                          'inverted-sphere background networks at 768x576')
@@ -179,15 +184,16 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n = max(32, min(args.cpu_rays * 2, 256))
-    steps = max(1, min(args.steps, 8))
-    r = cpu_train_steps(n, steps, min(args.warmup, 1))
+    n = args.ref_rays or args.rays          # the same config as this repo's arm: 1024 rays per step
+    steps = max(1, args.steps)
+    r = cpu_train_steps(n, steps, max(0, args.warmup))
     line = {
         'metric': 'rays/sec (fwd+bwd train step)', 'value': r['value'], 'unit': 'rays/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'steps': steps, 'warmup': max(0, args.warmup), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-        'config': {'workload': 'DTU VolSDF train step (BASELINE configs[1]) on host CPU cores, bounded sample of %d rays/step' % n,
-                   'rays_per_step': n},
+        'config': {'workload': 'DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
+                               'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam — the reference algorithm on the host CPU cores',
+                   'rays_per_gpu': n, 'global_rays': n, 'rays_per_step': n},
         'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': r['value'], 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -199,14 +205,265 @@ def run_reference(args):
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------
 
+ENGINE_TEXT = {
+    0: ('f32', 'fp32 SIMT (parity mode)'),
+    1: ('f16', 'tcgen05 kind::f16, single fp16 operands, fp32 TMEM accumulate (fastest; sdf ~1e-3: OUTSIDE the 1e-3 depth contract)'),
+    2: ('f16', 'tcgen05 kind::f16, split fp16 hi+lo operands (3 MMAs/layer) in every forward chain, single fp16 in the backward '
+               'chains, fp32 TMEM accumulate: rgb/depth <= 1e-3, parameter gradients <= 1e-2 vs the fp64 oracle (tests/test_gpu_split.py)'),
+}
+
+
+def pick_engine(args, L):
+    return {'auto': L.ENGINE_TC_SPLIT, 'tc_split': L.ENGINE_TC_SPLIT, 'tc': L.ENGINE_TC, 'fp32': L.ENGINE_FP32}[args.engine]
+
+
+class TrainRig(object):
+    """One DTU / BlendedMVS train step (forward + loss + backward [+ gradient all-reduce] + clip + Adam) at R rays per GPU:
+    eager closure, CUDA-graph replay, and the end-to-end variant with host inputs / host RNG / loss read-back."""
+
+    def __init__(self, args, R, engine, world, rank, dev, n_tapes, scene):
+        import svolsdf_b200._lib as L
+        import svolsdf_b200.conf as C
+        import svolsdf_b200.scene as S
+        from svolsdf_b200 import dist as sdist
+        from svolsdf_b200.model.network import VolSDFNetwork
+        from svolsdf_b200.model.ray_sampler import RecordedRng, RefRng, TapeRng
+        from svolsdf_b200.optim import FusedAdam
+        self.L, self.R, self.world, self.dev = L, R, world, dev
+        self.Rg = Rg = R * world
+        torch.manual_seed(0)
+        if scene == 'bmvs':
+            from svolsdf_b200.model.network_bg import VolSDFNetworkBG
+            model = VolSDFNetworkBG(C.bmvs_model_conf()).to(dev).train().set_engine(engine)
+        else:
+            model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
+        self.model = model
+        # clip_grad_norm_(1.0) + NaN guard + Adam of vsdf.py:214-219 as one fused step (svolsdf_b200.optim.FusedAdam)
+        self.opt = opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
+        self.reducer = reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
+        inp_host = S.make_input(scene, Rg, pixels='perm' if Rg > 4096 else 'random')
+        gt_host = S.gt_rgb(Rg)
+        lo, hi = sdist.shard_range(Rg, rank, world)
+        inp_host = sdist.shard_input(inp_host, rank, world)
+        gt_host = gt_host[:, lo:hi].contiguous()
+        self.inp_host, self.gt_host = inp_host, gt_host
+        self.inp_pin = {k: v.pin_memory() for k, v in inp_host.items()}
+        self.gt_pin = gt_host.pin_memory()
+        self.inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
+        self.gt_dev = gt_host.to(dev)
+        self.rng_mode = 'single' if world == 1 else ('global' if args.rng == 'global' else 'local')
+        rng_mode = self.rng_mode
+
+        def make_rng():
+            return sdist.ShardedRng(dev, Rg, lo, hi) if rng_mode == 'global' else RefRng(dev)
+        self.make_rng = make_rng
+        # random draws of every step, made in the reference's order and uploaded BEFORE the timed region
+        torch.manual_seed(1234 + (rank if rng_mode == 'local' else 0))
+        self.tapes = []
+        for _ in range(n_tapes):
+            tr = TapeRng(make_rng())
+            model.rng_source = tr
+            with torch.no_grad():   # a dry forward only to make the draws in the reference's order (not timed)
+                model(self.inp_dev, fast=1)
+            self.tapes.append(tr.tape)
+        model.rng_source = None
+        torch.cuda.synchronize()
+        self.RecordedRng = RecordedRng
+        l0 = L.launch_count()
+        self.step_eager(0)
+        torch.cuda.synchronize()
+        self.launches_per_step = L.launch_count() - l0
+        self.graphed, self.step_mode = None, 'eager'
+        if not args.eager:
+            try:
+                from svolsdf_b200.train import GraphedTrainStep
+                self.graphed = GraphedTrainStep(model, opt, self.loss_of, self.inp_dev, self.gt_dev, grad_clip=0.0,
+                                                reducer=reducer, world=world, make_rng=make_rng)
+                self.step_mode = 'cuda_graph'
+            except Exception as e:   # keep the run alive, say so in the JSON line
+                self.graphed, self.step_mode = None, 'eager (graph capture failed: %s)' % (str(e).splitlines()[0][:120],)
+                model.rng_source = None
+        self.pending = None
+
+    @staticmethod
+    def loss_of(out, gt):
+        return (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean() + \
+            0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
+
+    def finish(self, loss):
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.allreduce_(self.world)
+        self.opt.step()      # gradient clipping to norm 1.0 happens inside the fused step
+
+    def step_eager(self, i):
+        self.model.rng_source = self.RecordedRng(self.dev, self.tapes[i % len(self.tapes)])
+        out = self.model(self.inp_dev, fast=1)
+        self.finish(self.loss_of(out, self.gt_dev))
+
+    def step_device(self, i):
+        if self.graphed is not None:
+            self.graphed(draws=self.tapes[i % len(self.tapes)])     # inputs + this step's random draws already resident in HBM
+        else:
+            self.step_eager(i)
+
+    def step_e2e(self):
+        if self.graphed is not None:
+            # host RNG in the reference's order -> pinned -> device.  The draws of step i+1 are made on the CPU while
+            # the GPU replays step i (they only depend on the CPU generator), then the loss of step i is read back.
+            draws = self.pending if self.pending is not None else self.graphed.draw()
+            loss = self.graphed(self.inp_pin, self.gt_pin, draws)
+            self.pending = self.graphed.draw()
+            return float(loss.item()), self.graphed.h2d_bytes_rng
+        self.model.rng_source = self.make_rng()
+        inp = {k: v.to(self.dev, non_blocking=True) for k, v in self.inp_pin.items()}
+        gt = self.gt_pin.to(self.dev, non_blocking=True)
+        out = self.model(inp, fast=1)
+        loss = self.loss_of(out, gt)
+        self.finish(loss)
+        return float(loss.item()), self.model.rng_source.h2d_bytes   # device->host read of the step's result
+
+    def release(self):
+        self.graphed = None
+        self.model.rng_source = None
+
+
+def timed(fn, K, barrier, max_over_ranks):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        fn(i)
+    e1.record()
+    barrier()
+    return max_over_ranks(e0.elapsed_time(e1)) / K
+
+
+def parity_leg(engine, R=1024):
+    """Measured errors of the benchmarked engine at the benchmarked size against fp64 autograd on the oracle (same
+    sample positions): the numbers tests/test_gpu_split.py bounds by 1e-3 / 1e-2."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import build_model, conf_of, max_abs, rel_err, state_dict_cpu
+    from oracle import volsdf_oracle as O
+    import svolsdf_b200.scene as S
+    res = {}
+    for beta in (0.05, 0.01):
+        model = build_model('dtu', perturb=True, beta=beta, device='cuda').train().set_engine(engine)
+        sd = state_dict_cpu(model)
+        inp, gt = S.make_input('dtu', R), S.gt_rgb(R)
+        torch.manual_seed(321)
+        out = model({k: v.cuda() for k, v in inp.items()}, fast=1)
+        loss = TrainRig.loss_of(out, gt.cuda())
+        model.zero_grad()
+        loss.backward()
+        ref = {k: v.double().clone().requires_grad_(True) for k, v in sd.items()}
+        z, z_eik = model.last_z
+        torch.manual_seed(321)
+        rng = O.draw_rng(R, True)
+        o = O.volsdf_forward(ref, conf_of('dtu'), inp, True, fast=1, rng=rng, dtype=torch.float64,
+                             z_override=(z.cpu(), z_eik.cpu(), None))
+        O.volsdf_loss(o, gt).backward()
+        worst = max(rel_err(p.grad.cpu(), ref[n].grad) for n, p in model.named_parameters()
+                    if ref[n].grad is not None and float(ref[n].grad.norm()) > 1e-10)
+        res['beta_%g' % beta] = {'rgb_max_abs': max_abs(out['rgb_values'].detach().cpu(), o['rgb_values'].detach()),
+                                 'depth_max_abs': max_abs(out['depth_values'].detach().cpu(), o['depth_values'].detach()),
+                                 'worst_param_grad_rel': worst}
+    return {'rays': R, 'against': 'fp64 autograd on oracle/volsdf_oracle.py, same sample positions', 'errors': res,
+            'bounds': {'rgb/depth max-abs': 1e-3, 'param grad rel': 1e-2}}
+
+
+def gpu_eager_leg(R, steps=3):
+    """the reference algorithm as plain PyTorch eager fp32 on the B200 — the implementation to beat.  The
+    reference itself when /root/reference is mounted (this container has no GPU; the GPU box has no /root/reference), else
+    the oracle's restatement of it, run on cuda:0 with TF32 off."""
+    import svolsdf_b200.conf as C
+    import svolsdf_b200.scene as S
+    from oracle import volsdf_oracle as O
+    from svolsdf_b200.model.network import VolSDFNetwork
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device('cuda', torch.cuda.current_device())
+    torch.manual_seed(0)
+    m = VolSDFNetwork(C.dtu_model_conf())
+    with torch.device(dev):   # the oracle creates its constants / random draws with bare factory calls
+        sd = {k: v.detach().to(dev).clone().requires_grad_(True) for k, v in m.state_dict().items()}
+        opt = torch.optim.Adam(list(sd.values()), lr=5e-4)
+        conf = C.dtu_model_conf()
+    inp = {k: v.to(dev) for k, v in S.make_input('dtu', R).items()}
+    gt = S.gt_rgb(R).to(dev)
+    with torch.device(dev):
+
+        def step():
+            out = O.volsdf_forward(sd, conf, inp, True, fast=1)
+            loss = O.volsdf_loss(out, gt)
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
+            opt.step()
+            return loss
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        float(loss)
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': R / (ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms, 'kind': 'port',
+            'what': 'oracle/volsdf_oracle.py (restatement of the reference, plain PyTorch ops) on cuda:0, fp32 eager, TF32 off, '
+                    '%d rays, fwd+loss+bwd+clip+Adam, 1 warm-up + %d timed' % (R, steps)}
+
+
+def frame_leg(args, engine, world, rank, dev, barrier, max_over_ranks):
+    """BASELINE configs[2]: 1600x1200 DTU full-image render (rgb + depth + normal), ray-sharded over the ranks, 512-ray
+    convergence groups inside every launch chunk (= the reference's chunked render loop ray for ray)."""
+    import svolsdf_b200.conf as C
+    import svolsdf_b200.scene as S
+    from svolsdf_b200.model.network import VolSDFNetwork
+    from svolsdf_b200.render import render_image
+    torch.manual_seed(0)
+    model = VolSDFNetwork(C.dtu_model_conf())
+    beta = 0.01 if args.beta is None else args.beta
+    S.perturb_(model, w_std=0.0, b_std=0.0, beta=beta)
+    model = model.to(dev).eval().set_engine(engine)
+    Wd, Ht = 1600, 1200
+    inp = S.make_input('dtu', Wd * Ht, width=Wd, height=Ht, pixels='grid')
+    K_, pose, uv = inp['intrinsics'].to(dev), inp['pose'].to(dev), inp['uv'].to(dev)
+    R = uv.shape[1]
+    torch.manual_seed(7)
+    out = render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world, group=args.group)   # warm-up
+    nf = 1 if world == 1 else 2
+    ms = timed(lambda i: render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world, group=args.group),
+               nf, barrier, max_over_ranks)
+    iters = out['sampler_iters']
+    mean_it = sum(iters) / max(len(iters), 1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([float(sum(iters)), float(len(iters))], device=dev)
+        dist.all_reduce(t)
+        mean_it = float(t[0] / t[1])
+    pk = peaks()
+    flop = R * (mean_it * 128 * F_SDF + 98 * (2 * F_SDF + F_RENDER))
+    tf = flop / (ms * 1e-3) / 1e12
+    return {'metric': 'ms/frame 1600x1200 render', 'value': ms, 'unit': 'ms/frame', 'higher_is_better': False,
+            'scaling': 'strong', 'rays': R, 'rays_per_s': R / (ms * 1e-3), 'frames_timed': nf, 'beta': beta,
+            'chunk_rays': args.chunk, 'convergence_group_rays': args.group, 'sampler_iterations_mean': mean_it,
+            'parallelism': 'ray-sharded dp%d (512-ray groups stay on one rank) + all-gather of 28 B/ray' % world,
+            'roofline': {'bound': 'tensor', 'achieved': tf / world, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                         'frac': tf / world / pk['tflops_sustained'], 'traffic': None,
+                         'kernel': 'whole frame (algorithmic FLOP: I*128 F + 98 (2 F + F_r) per ray, I = mean sampler iterations)'},
+            'rgb_mean': float(out['rgb_values'].mean()), 'depth_mean': float(out['depth_values'].mean())}
+
+
+MLP_KERNELS = ('mlp_',)
+
+
 def run_ours(args):
     import torch.distributed as dist
     import svolsdf_b200._lib as L
-    import svolsdf_b200.conf as C
-    import svolsdf_b200.scene as S
-    from svolsdf_b200 import dist as sdist
-    from svolsdf_b200.model.network import VolSDFNetwork
-    from svolsdf_b200.model.ray_sampler import RecordedRng, RefRng, TapeRng
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -218,107 +475,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     L.load()
-    engine = L.ENGINE_FP32
-    if args.engine == 'tc' or (args.engine == 'auto' and L.load().svs_has_engine(L.ENGINE_TC)):
-        engine = L.ENGINE_TC
+    engine = pick_engine(args, L)
     K, W, R = args.steps, max(args.warmup, 3), args.rays
-    Rg = R * world
-
-    torch.manual_seed(0)
-    bmvs = args.scene == 'bmvs'
-    if bmvs:
-        from svolsdf_b200.model.network_bg import VolSDFNetworkBG
-        model = VolSDFNetworkBG(C.bmvs_model_conf()).to(dev).train().set_engine(engine)
-    else:
-        model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
-    # clip_grad_norm_(1.0) + NaN guard + Adam of vsdf.py:214-219 as one fused step (svolsdf_b200.optim.FusedAdam)
-    from svolsdf_b200.optim import FusedAdam
-    opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
-    reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
-    inp_host = S.make_input(args.scene, Rg, pixels='perm' if Rg > 4096 else 'random')
-    gt_host = S.gt_rgb(Rg)
-    lo, hi = sdist.shard_range(Rg, rank, world)
-    inp_host = sdist.shard_input(inp_host, rank, world)
-    gt_host = gt_host[:, lo:hi].contiguous()
-    inp_pin = {k: v.pin_memory() for k, v in inp_host.items()}
-    gt_pin = gt_host.pin_memory()
-    inp_dev = {k: v.to(dev) for k, v in inp_host.items()}
-    gt_dev = gt_host.to(dev)
-
-    def loss_of(out, gt):
-        return (out['rgb_values'] - gt.reshape(-1, 3)).abs().mean() + \
-            0.1 * ((out['grad_theta'].norm(2, dim=1) - 1) ** 2).mean()
-
-    def finish(loss):
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if reducer is not None:
-            reducer.allreduce_(world)
-        opt.step()      # gradient clipping to norm 1.0 happens inside the fused step
-
-    rng_mode = 'single' if world == 1 else ('global' if args.rng == 'global' else 'local')
-
-    def make_rng():
-        return sdist.ShardedRng(dev, Rg, lo, hi) if rng_mode == 'global' else RefRng(dev)
-
-    # random draws of every step, made in the reference's order and uploaded BEFORE the timed region
-    torch.manual_seed(1234 + (rank if rng_mode == 'local' else 0))
-    tapes = []
+    skip = set(filter(None, args.skip.split(',')))
+    if args.workload == 'train':
+        skip |= {'frame', 'large'}
     n_prof = 2
-    for _ in range(W + max(K, n_prof)):
-        tr = TapeRng(make_rng())
-        model.rng_source = tr
-        with torch.no_grad():   # a dry forward only to make the draws in the reference's order (not timed)
-            model(inp_dev, fast=1)
-        tapes.append(tr.tape)
-    model.rng_source = None
-    torch.cuda.synchronize()
-
-    def step_eager(i):
-        model.rng_source = RecordedRng(dev, tapes[i])
-        out = model(inp_dev, fast=1)
-        finish(loss_of(out, gt_dev))
-
-    # launches of this library per step (counted on one eager step; a graph replay re-issues exactly these)
-    l0 = L.launch_count()
-    step_eager(0)
-    torch.cuda.synchronize()
-    launches_per_step = L.launch_count() - l0
-
-    graphed, step_mode = None, 'eager'
-    if not args.eager:
-        try:
-            from svolsdf_b200.train import GraphedTrainStep
-            graphed = GraphedTrainStep(model, opt, loss_of, inp_dev, gt_dev, grad_clip=0.0, reducer=reducer, world=world,
-                                       make_rng=make_rng)
-            step_mode = 'cuda_graph'
-        except Exception as e:   # keep the run alive, say so in the JSON line
-            graphed, step_mode = None, 'eager (graph capture failed: %s)' % (str(e).splitlines()[0][:120],)
-            model.rng_source = None
-
-    def step_device(i):
-        if graphed is not None:
-            graphed(draws=tapes[i])     # inputs + this step's random draws already resident in HBM
-        else:
-            step_eager(i)
-
-    pending = {'draws': None}
-
-    def step_e2e():
-        if graphed is not None:
-            # host RNG in the reference's order -> pinned -> device.  The draws of step i+1 are made on the CPU while
-            # the GPU replays step i (they only depend on the CPU generator), then the loss of step i is read back.
-            draws = pending['draws'] if pending['draws'] is not None else graphed.draw()
-            loss = graphed(inp_pin, gt_pin, draws)
-            pending['draws'] = graphed.draw()
-            return float(loss.item()), graphed.h2d_bytes_rng
-        model.rng_source = make_rng()
-        inp = {k: v.to(dev, non_blocking=True) for k, v in inp_pin.items()}
-        gt = gt_pin.to(dev, non_blocking=True)
-        out = model(inp, fast=1)
-        loss = loss_of(out, gt)
-        finish(loss)
-        return float(loss.item()), model.rng_source.h2d_bytes   # device->host read of the step's result
+    bmvs = args.scene == 'bmvs'
 
     def barrier():
         if world > 1:
@@ -332,47 +495,41 @@ def run_ours(args):
             return float(t.item())
         return ms
 
+    rig = TrainRig(args, R, engine, world, rank, dev, W + max(K, n_prof), args.scene)
+    Rg = rig.Rg
+    step_mode = rig.step_mode
+
     # ---- device-timed region: inputs resident in HBM ----
     for i in range(W):
-        step_device(i)
+        rig.step_device(i)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        step_device(W + i)
-    e1.record()
-    barrier()
-    launches = launches_per_step * K
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = timed(lambda i: rig.step_device(W + i), K, barrier, max_over_ranks)
     clk = clocks.stop()
-    ms_step = ms_total / K
+    launches = rig.launches_per_step * K
     value = Rg / (ms_step * 1e-3)
 
     # ---- end-to-end region: host buffers + host RNG + loss read-back every step ----
-    torch.manual_seed(99 + (rank if rng_mode == 'local' else 0))
+    torch.manual_seed(99 + (rank if rig.rng_mode == 'local' else 0))
     for _ in range(3):
-        step_e2e()
-    barrier()
-    h2d = 0
-    e0.record()
-    for _ in range(K):
-        _, nb = step_e2e()
-        h2d = nb
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / K
-    h2d_bytes = h2d + sum(v.numel() * v.element_size() for v in inp_pin.values()) + gt_pin.numel() * 4
+        rig.step_e2e()
+    h2d = [0]
+
+    def e2e_step(i):
+        _, nb = rig.step_e2e()
+        h2d[0] = nb
+    ms_e2e = timed(e2e_step, K, barrier, max_over_ranks)
+    h2d_bytes = h2d[0] + sum(v.numel() * v.element_size() for v in rig.inp_pin.values()) + rig.gt_pin.numel() * 4
 
     # ---- per-kernel profile pass (CUDA events around every launch of the library; not part of the timing) ----
     L.prof_enable(True)
     for i in range(n_prof):
-        step_eager(W + i)
+        rig.step_eager(W + i)
     torch.cuda.synchronize()
     prof = L.prof_collect()
     L.prof_enable(False)
-    model.rng_source = None
+    rig.model.rng_source = None
     pk = peaks()
     roofline, rooflines, kernels = None, [], {}
     traffic_tab = {}
@@ -384,9 +541,12 @@ def run_ours(args):
         for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             kernels[name] = {'launches_per_step': v['launches'] / n_prof, 'ms_per_step': v['ms'] / n_prof,
                              'share_of_kernel_time': v['ms'] / tot_ms}
+
         def entry(name, v):
-            """both rooflines of one kernel; `bound` = the one it sits closer to.  achieved = ALGORITHMIC flops / bytes
-            (SURVEY.md 8d figures, passed by the library with every launch) over the CUDA-event time."""
+            """MLP kernels (dense contractions) are reported on the TENSOR roofline, sampler / compositor /
+            ray kernels on the HBM roofline; the other fraction rides along.  achieved = ALGORITHMIC flops / bytes (8d
+            figures, passed by the library with every launch; split-operand chains count their flops once, not 3x) over
+            the live CUDA-event time."""
             sec = v['ms'] * 1e-3
             tf = v['flops'] / sec / 1e12 if v['flops'] > 0 else 0.0
             gb = v['bytes'] / sec / 1e9 if v['bytes'] > 0 else 0.0
@@ -394,79 +554,116 @@ def run_ours(args):
             tr = traffic_tab.get(name)
             e = {'kernel': name, 'avg_launch_ms': v['ms'] / v['launches'], 'traffic': tr,
                  'tensor_frac': f_t, 'hbm_frac': f_h if gb > 0 else None,
-                 # measured DRAM bytes (ncu, per launch) over the live launch time: how close the kernel is to the HBM
-                 # roofline counting everything it actually moves (saved activation tiles included)
                  'hbm_frac_measured_traffic': (tr / (v['ms'] / v['launches'] * 1e-3) / 1e9 / pk['hbm_gbs']) if tr else None}
-            if f_h > f_t:
-                e.update({'bound': 'hbm', 'achieved': gb, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': f_h,
-                          'peak_source': pk['source']})
-            else:
+            if name.startswith(MLP_KERNELS) and v['flops'] > 0:
                 e.update({'bound': 'tensor', 'achieved': tf, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                           'frac': f_t, 'peak_source': pk['source'] + ' bf16 sustained'})
+            else:
+                e.update({'bound': 'hbm', 'achieved': gb, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': f_h,
+                          'peak_source': pk['source']})
             return e
         name, v = max(prof.items(), key=lambda kv: kv[1]['ms'])
         roofline = entry(name, v)
         rooflines = [entry(n_, v_) for n_, v_ in sorted(prof.items(), key=lambda kv: -kv[1]['ms']) if v_['flops'] > 0 or v_['bytes'] > 0]
 
-    # ---- the fp32 parity engine on the same step, for reference (not the headline) ----
-    parity = None
-    if engine != L.ENGINE_FP32 and world == 1 and not args.no_parity_leg:
-        model.set_engine(L.ENGINE_FP32)
+    # ---- the other engines on the same step, eager, for context (not the headline) ----
+    other = {}
+    if world == 1 and 'engines' not in skip:
+        for ename, e in (('tc_single_fp16', L.ENGINE_TC), ('fp32_simt', L.ENGINE_FP32)):
+            if e == engine:
+                continue
+            rig.model.set_engine(e)
+            for i in range(2):
+                rig.step_eager(i)
+            ms_o = timed(lambda i: rig.step_eager(W + i), 3, barrier, max_over_ranks)
+            other[ename] = {'ms_per_step_eager': ms_o, 'rays_per_s': Rg / (ms_o * 1e-3), 'engine': ENGINE_TEXT[e][1]}
+        rig.model.set_engine(engine)
         for i in range(2):
-            step_eager(i)
-        torch.cuda.synchronize()
-        e0.record()
+            rig.step_eager(i)
+        ms_o = timed(lambda i: rig.step_eager(W + i), 3, barrier, max_over_ranks)
+        other['benchmarked_engine_eager'] = {'ms_per_step_eager': ms_o, 'rays_per_s': Rg / (ms_o * 1e-3)}
+    rig.release()
+    del rig
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: large-batch data-parallel step, 8192 rays per GPU (65536 over 8 GPUs) ----
+    large = None
+    if 'large' not in skip and not bmvs:
+        Kl = max(3, min(K, 10))
+        big = TrainRig(args, args.large_rays, engine, world, rank, dev, 3 + Kl, 'dtu')
         for i in range(3):
-            step_eager(W + i % max(K, n_prof))
-        e1.record()
-        torch.cuda.synchronize()
-        parity = {'engine': 'fp32 SIMT (parity mode)', 'ms_per_step': e0.elapsed_time(e1) / 3,
-                  'rays_per_s': Rg / (e0.elapsed_time(e1) / 3 * 1e-3)}
-        model.set_engine(engine)
-    model.rng_source = None
+            big.step_device(i)
+        ms_big = timed(lambda i: big.step_device(3 + i), Kl, barrier, max_over_ranks)
+        tfl = FLOP_PER_RAY_TRAIN * big.Rg / (ms_big * 1e-3) / 1e12
+        large = {'workload': 'BASELINE configs[4]: data-parallel DTU train step, %d rays per GPU = %d rays per step over %d GPU(s), '
+                             'NCCL all-reduce of the flat fp32 gradients inside the graph' % (args.large_rays, big.Rg, world),
+                 'rays_per_gpu': args.large_rays, 'global_rays': big.Rg, 'value': big.Rg / (ms_big * 1e-3), 'unit': 'rays/s',
+                 'ms_per_step': ms_big, 'steps': Kl, 'warmup': 3, 'step_mode': big.step_mode, 'scaling': 'weak',
+                 'algorithmic_tflops': tfl, 'algorithmic_frac_of_tensor_peak': tfl / world / pk['tflops_sustained']}
+        big.release()
+        del big
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2]: full frame ----
+    frame = None
+    if 'frame' not in skip and not bmvs:
+        frame = frame_leg(args, engine, world, rank, dev, barrier, max_over_ranks)
 
     def leave():
-        """End of a multi-rank run.  destroy_process_group() was seen to block forever once the communicator has been
-        used inside a captured CUDA graph (2-GPU run: the JSON line was out, both ranks sat in the destructor until the
-        launcher's timeout): drop the graph, drain the device, meet once more, then leave without the destructor."""
-        nonlocal graphed
-        graphed = None
+        """End of a multi-rank run: the NCCL communicator was used inside captured graphs; all graphs are released above,
+        the device is drained and the ranks meet once more before the group is destroyed."""
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        if os.environ.get('SVS_BENCH_DESTROY_PG', '0') == '1':
+            dist.destroy_process_group()
+        else:
+            os._exit(0)
 
     if rank != 0:
         if world > 1:
             leave()
         return
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_train_steps(args.cpu_rays, 2, 1)
-        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    cpu = parity = gpu_eager = None
+    if world == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_train_steps(args.cpu_rays, 2, 1)
+            cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        if 'parity' not in skip and not bmvs:
+            try:
+                parity = parity_leg(engine, 1024)
+            except Exception as e:
+                parity = {'error': str(e).splitlines()[0][:200]}
+        if 'gpu_eager' not in skip and not bmvs:
+            try:
+                gpu_eager = gpu_eager_leg(R)
+            except Exception as e:
+                gpu_eager = {'error': str(e).splitlines()[0][:200]}
     # BMVS: 128F + 97(6F+3F_r) + 32(3F_bg+3F_br) + 12F per ray (SURVEY.md 8d)
     step_tflops = (1020432384.0 if bmvs else FLOP_PER_RAY_TRAIN) * Rg / (ms_step * 1e-3) / 1e12
     line = {
         'metric': 'rays/sec (fwd+bwd train step)', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
         'warmup': W, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16' if engine == L.ENGINE_TC else 'f32', 'data': 'synthetic',
+        'dtype': ENGINE_TEXT[engine][0], 'data': 'synthetic',
         'config': {'workload': ('BlendedMVS VolSDFNetworkBG train step fwd+bwd+eikonal (BASELINE configs[3]): sampler 128 + main 97 + '
                                 'eikonal 2 SDF evals + 32 inverted-sphere background samples/ray, L1+0.1*eik loss, clip+Adam') if bmvs else
                                ('DTU VolSDF train step fwd+bwd+eikonal (BASELINE configs[1]): sampler 128 + main 98 + '
                                 'eikonal 2 SDF evals/ray, L1+0.1*eik loss, clip+Adam'), 'rays_per_gpu': R,
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
-                   'engine': 'tcgen05 kind::f16 (fp16 operands, fp32 TMEM accumulate)' if engine == L.ENGINE_TC else 'fp32 SIMT (parity mode)',
+                   'engine': ENGINE_TEXT[engine][1],
                    'step_mode': step_mode,
                    'host_rng': {'single': 'reference order, CPU default generator', 'local': 'per-rank CPU streams (seed + rank)',
-                                'global': 'global-batch draws on every rank, rows sliced (sharded == unsharded per ray)'}[rng_mode]},
+                                'global': 'global-batch draws on every rank, rows sliced (sharded == unsharded per ray)'}[
+                                    'single' if world == 1 else ('global' if args.rng == 'global' else 'local')]},
         'e2e': {'value': Rg / (ms_e2e * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms_e2e,
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         'algorithmic_tflops': step_tflops, 'algorithmic_frac_of_tensor_peak': step_tflops * 1.0 / world / pk['tflops_sustained'],
-        'kernels': kernels, 'rooflines': rooflines, 'parity_engine': parity,
+        'parity': parity, 'gpu_eager_baseline': gpu_eager, 'frame': frame, 'large_batch': large,
+        'kernels': kernels, 'rooflines': rooflines, 'other_engines': other,
     }
     print(json.dumps(line))
     if world > 1:
@@ -477,14 +674,9 @@ F_SDF, F_RENDER = 1049088.0, 533504.0   # FLOP per point-forward, SURVEY.md Appe
 
 
 def run_frame(args):
-    """BASELINE configs[2]: 1600x1200 DTU full-image render (rgb + depth + normal), ray-sharded over the ranks."""
+    """`--workload frame`: only BASELINE configs[2] (the default run carries the same numbers under `frame`)."""
     import torch.distributed as dist
     import svolsdf_b200._lib as L
-    import svolsdf_b200.conf as C
-    import svolsdf_b200.scene as S
-    from svolsdf_b200.model.network import VolSDFNetwork
-    from svolsdf_b200.render import render_image
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -494,58 +686,30 @@ def run_frame(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    engine = L.ENGINE_FP32 if args.engine == 'fp32' else L.ENGINE_TC
-    torch.manual_seed(0)
-    model = VolSDFNetwork(C.dtu_model_conf())
-    if args.beta is not None:
-        S.perturb_(model, w_std=0.0, b_std=0.0, beta=args.beta)
-    model = model.to(dev).eval().set_engine(engine)
-    Wd, Ht = 1600, 1200
-    inp = S.make_input('dtu', Wd * Ht, width=Wd, height=Ht, pixels='grid')
-    K_, pose, uv = inp['intrinsics'].to(dev), inp['pose'].to(dev), inp['uv'].to(dev)
-    R = uv.shape[1]
-    K, W = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    L.load()
+    engine = pick_engine(args, L)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    torch.manual_seed(7)
-    for _ in range(W):
-        out = render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world)
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
     clocks = ClockSampler(local)
-    barrier()
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        out = render_image(model, K_, pose, uv, chunk=args.chunk, rank=rank, world=world)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / K
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    fr = frame_leg(args, engine, world, rank, dev, barrier, max_over_ranks)
     clk = clocks.stop()
-    iters = out['sampler_iters']
     if rank == 0:
-        pk = peaks()
-        mean_it = sum(iters) / max(len(iters), 1)
-        flop = R * (mean_it * 128 * F_SDF + 98 * (2 * F_SDF + F_RENDER))
-        tf = flop / (ms * 1e-3) / 1e12
-        print(json.dumps({
-            'metric': 'ms/frame 1600x1200 render', 'value': ms, 'unit': 'ms/frame', 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': ms, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None,
-            'dtype': 'f16' if engine == L.ENGINE_TC else 'f32', 'data': 'synthetic',
-            'config': {'workload': 'DTU 1600x1200 full-image render (BASELINE configs[2]): rgb + depth + normal, %d rays, '
-                                   'chunks of %d rays per model call' % (R, args.chunk), 'beta': args.beta,
-                       'sampler_iterations_mean': mean_it, 'parallelism': 'ray-sharded dp%d + all-gather of 28 B/ray' % world},
-            'rays_per_s': R / (ms * 1e-3), 'clocks': clk,
-            'roofline': {'bound': 'tensor', 'achieved': tf / world, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                         'frac': tf / world / pk['tflops_sustained'], 'traffic': None, 'kernel': 'whole frame (algorithmic FLOP)'},
-            'rgb_mean': float(out['rgb_values'].mean()), 'depth_mean': float(out['depth_values'].mean())}))
+        fr.update({'n_gpus': world, 'steps': fr['frames_timed'], 'warmup': 1, 'ms_per_step': fr['value'], 'vs_baseline': None,
+                   'dtype': ENGINE_TEXT[engine][0], 'data': 'synthetic', 'clocks': clk,
+                   'config': {'workload': 'DTU 1600x1200 full-image render (BASELINE configs[2]): rgb + depth + normal',
+                              'engine': ENGINE_TEXT[engine][1]}})
+        print(json.dumps(fr))
     if world > 1:
         dist.destroy_process_group()
 

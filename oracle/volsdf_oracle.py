@@ -542,6 +542,9 @@ def volsdf_forward(sd, conf, inp, training, fast=-1, rng=None, dtype=torch.float
     beta = get_beta(sdd['density.beta'], beta_min)
     weights = volume_rendering(zc, sdf, beta)
     rgb_values, depth_values, _ = composite(weights, rgb, zc, depth_scale.to(dtype))
+    if white:   # white background assumption (network.py:244-247)
+        bg = torch.tensor(conf.get_list('bg_color', default=[1.0, 1.0, 1.0]), dtype=dtype)
+        rgb_values = rgb_values + (1.0 - weights.sum(-1, keepdim=True)) * bg.unsqueeze(0)
     out = {'rgb_values': rgb_values, 'depth_values': depth_values, 'depth_vals': zc * depth_scale.to(dtype),
            'weights': weights, 'xyz': pts, 'z_vals': z, 'sdf': sdf, 'gradients': grad, 'rgb': rgb,
            'trace': trace}

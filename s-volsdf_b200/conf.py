@@ -112,9 +112,13 @@ _BMVS_MODEL = {
 }
 
 
-def dtu_model_conf():
-    """`model:` block of config/vol/dtu.yaml."""
-    return _wrap(copy.deepcopy(_DTU_MODEL))
+def dtu_model_conf(white_bkgd=False, bg_color=(1.0, 1.0, 1.0)):
+    """`model:` block of config/vol/dtu.yaml; `white_bkgd` / `bg_color` are the optional keys network.py:196-198 reads."""
+    d = copy.deepcopy(_DTU_MODEL)
+    if white_bkgd:
+        d['white_bkgd'] = True
+        d['bg_color'] = list(bg_color)
+    return _wrap(d)
 
 
 def bmvs_model_conf():

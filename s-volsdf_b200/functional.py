@@ -19,6 +19,15 @@ def _contig(t):
     return None if t is None else t.contiguous()
 
 
+# Bumped by optimisers that update parameters through raw pointers (svolsdf_b200.optim.FusedAdam): torch's per-tensor
+# version counters do not see those writes, and NetHandle.prepare() caches the packed weights per (epoch, versions).
+_WEIGHTS_EPOCH = [0]
+
+
+def weights_changed():
+    _WEIGHTS_EPOCH[0] += 1
+
+
 class NetHandle(object):
     """Descriptor + parameter plumbing of one MLP (built once per nn.Module)."""
 
@@ -29,7 +38,11 @@ class NetHandle(object):
         self.wbuf_floats = int(L.load().svs_mlp_wbuf_floats(desc, engine))
         if self.wbuf_floats < 0:
             raise L.SvsError('bad MLP descriptor: %s' % L.load().svs_last_error().decode())
+        # the gradient accumulator shares the fp32 part of the layout (effective weights + biases); the packed fp16 images
+        # behind it exist only in wbuf
+        self.dwbuf_floats = int(L.load().svs_mlp_wbuf_floats(desc, L.ENGINE_FP32))
         self.ldy = int(L.load().svs_sdf_ldy(desc))
+        self._cache_key, self._cache_wbuf = None, None
 
     def flat_params(self):
         out = []
@@ -59,9 +72,18 @@ class NetHandle(object):
         return L.make_params(gs, vs, bs)
 
     def prepare(self, device):
+        """Effective weights (weight-norm applied) + packed operand images.  The reference recomputes W = g v / |v| in
+        a pre-forward hook on EVERY call (network.py:64-65); here the packed buffer is reused until a parameter changes
+        (one pack per optimiser step instead of one per entry point: sampler pass, main pass, rendering net ...).  A new
+        buffer is allocated per pack, so buffers saved for a backward are never overwritten."""
+        key = (_WEIGHTS_EPOCH[0], str(device), torch.cuda.is_current_stream_capturing() if torch.cuda.is_available() else False,
+               tuple((p.data_ptr(), p._version) for p in self.flat_params()))
+        if key == self._cache_key:
+            return self._cache_wbuf
         wbuf = _f32(self.wbuf_floats, device=device)
         ps = self.params_struct()
         L.call('svs_mlp_prepare', self.desc, ps, ptr(wbuf), self.engine, L.stream())
+        self._cache_key, self._cache_wbuf = key, wbuf
         return wbuf
 
     def param_grads(self, wbuf, dwbuf):
@@ -127,7 +149,7 @@ class SdfOutputsFn(torch.autograd.Function):
         x, y, saved, wbuf = ctx.saved_tensors
         dev = x.device
         lib = L.load()
-        dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
+        dwbuf = torch.zeros(net.dwbuf_floats, dtype=torch.float32, device=dev)
         ws = _f32(max(1, int(lib.svs_sdf_bwd_ws_floats(net.desc, P, net.engine))), device=dev)
         dy, d_sdf, d_grad = _contig(dy), _contig(d_sdf), _contig(d_grad)
         if not ctx.want_grad:
@@ -178,10 +200,19 @@ class RenderFn(torch.autograd.Function):
         saved, rgb, wbuf = ctx.saved_tensors
         dev = rgb.device
         lib = L.load()
-        dwbuf = torch.zeros(net.wbuf_floats, dtype=torch.float32, device=dev)
+        dwbuf = torch.zeros(net.dwbuf_floats, dtype=torch.float32, device=dev)
         ws = _f32(max(1, int(lib.svs_render_ws_floats(net.desc, P, net.engine))), device=dev)
         d_normals = _f32(P, 3, device=dev) if ctx.idr else None
-        d_feat = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=dev)
+        # the kernel writes the F feature columns; only the columns around them (the sdf column / row padding of the SDF
+        # net's y when the features are read in place) need zeros — not a fill of the whole (P, ldy) tensor
+        d_feat = torch.empty(ctx.feat_shape, dtype=torch.float32, device=dev)
+        F_ = net.desc.in_dim[0] - (3 * (1 + 2 * net.desc.n_freqs) + (6 if ctx.idr else 0))
+        if ctx.feat_col > 0:
+            d_feat[:, :ctx.feat_col].zero_()
+        if ctx.feat_col + F_ < d_feat.shape[1]:
+            d_feat[:, ctx.feat_col + F_:].zero_()
+        if d_feat.shape[0] > P:      # rows behind the rendered points (the eikonal samples ride at the tail of y)
+            d_feat[P:].zero_()
         L.call('svs_render_backward', net.desc, ptr(wbuf), P, ptr(saved), ptr(rgb), ptr(d_rgb.contiguous()),
                ptr(d_normals), d_feat.data_ptr() + 4 * ctx.feat_col, d_feat.stride(0), ptr(dwbuf), ptr(ws),
                net.engine, L.stream())

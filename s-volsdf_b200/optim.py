@@ -2,8 +2,14 @@
 reference's NaN/Inf guard and the Adam update for all parameter tensors in two launches
 (volsdf/vsdf.py:214-219,454-464 issue clip_grad_norm_, one isnan/isinf host sync per parameter, and Adam.step).
 
-State layout (`exp_avg`, `exp_avg_sq`, `step` as a device tensor) and `state_dict()` are those of
-`torch.optim.Adam(capturable=True)`, so the reference's optimizer checkpoints load unchanged.  CUDA-graph safe.
+State layout (`exp_avg`, `exp_avg_sq`, `step`) and `state_dict()` are those of `torch.optim.Adam`; `load_state_dict`
+accepts the reference's checkpoints (plain `torch.optim.Adam` state: `step` an int (torch 1.9) or a CPU tensor,
+`capturable` absent or False) and normalises them to what the kernel needs — `step` as a float32 scalar on the
+parameter's device, `capturable=True`.  CUDA-graph safe.
+
+Guard semantics (volsdf/vsdf.py:454-464 under the reference's pinned torch 1.9): non-finite gradients are zeroed and Adam
+still steps (moments decay, the step count advances).  All tensors of a group must receive a gradient in the same steps
+(the kernel takes one step count per group; the VolSDF models always do).
 """
 import ctypes as C
 
@@ -19,6 +25,30 @@ class FusedAdam(torch.optim.Adam):
         self.skip_nonfinite = bool(skip_nonfinite)
         self._scratch = None
         self.last_grad_norm_sq = None   # device tensor: sum of squared gradients of the last step (before clipping)
+
+    def _normalise_state(self):
+        for group in self.param_groups:
+            group['capturable'] = True
+            group['foreach'] = False
+            group['fused'] = None
+            for p in group['params']:
+                st = self.state.get(p)
+                if not st:
+                    continue
+                step = st.get('step', 0)
+                step = float(step.item()) if torch.is_tensor(step) else float(step)
+                st['step'] = torch.full((), step, dtype=torch.float32, device=p.device)
+                for k in ('exp_avg', 'exp_avg_sq'):
+                    if k in st:
+                        st[k] = st[k].to(device=p.device, dtype=torch.float32).contiguous()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._normalise_state()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._normalise_state()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -44,6 +74,9 @@ class FusedAdam(torch.optim.Adam):
             if self._scratch is None or self._scratch.device != dev:
                 self._scratch = torch.zeros(2, dtype=torch.float32, device=dev)
             steps = [self.state[p]['step'] for p in ps]
+            if not all(t.is_cuda and t.dtype == torch.float32 for t in steps):
+                self._normalise_state()          # state injected behind load_state_dict's back
+                steps = [self.state[p]['step'] for p in ps]
             torch._foreach_add_(steps, 1.0)      # every tensor of a group carries the same count, as in torch
             n = len(ps)
             arr = C.c_void_p * n
@@ -55,4 +88,6 @@ class FusedAdam(torch.optim.Adam):
                    self.max_grad_norm, 1 if self.skip_nonfinite else 0, steps[0].data_ptr(), self._scratch.data_ptr(),
                    L.stream())
             self.last_grad_norm_sq = self._scratch[0]
+        from . import functional as F_
+        F_.weights_changed()      # parameters were written through raw pointers: invalidate the packed-weight caches
         return loss

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     p = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
-                        '--cpu-rays', '32'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        '--ref-rays', '32'], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['metric'].startswith('rays/sec') and line['unit'] == 'rays/s'

@@ -251,3 +251,83 @@ def test_state_dict_roundtrip_and_optimizer_step():
     torch.manual_seed(3)
     b = m2(inp)
     assert torch.equal(a['rgb_values'], b['rgb_values'])
+
+
+@pytest.mark.parametrize('engine', PARITY_ENGINES)
+def test_white_background_vs_reference_golden(engine):
+    """`white_bkgd: true` (network.py:196-200,244-247): no sphere clamp, rgb += (1 - sum w) * bg_color; against the
+    reference's recorded eval output (rays that miss the object accumulate as little as 0.016)"""
+    import svolsdf_b200.conf as C
+    from svolsdf_b200.model.network import VolSDFNetwork
+    g = load_golden('dtu_white_bkgd_r32')
+    torch.manual_seed(0)
+    m = VolSDFNetwork(C.dtu_model_conf(white_bkgd=True, bg_color=(1.0, 0.5, 0.25)))
+    S.perturb_(m, seed=7, w_std=S.PERTURB_W, b_std=S.PERTURB_B, beta=0.05)
+    assert abs(float(sum(p.detach().double().sum() for p in m.parameters())) - float(g['meta/param_sum'])) < 1e-6
+    m = m.to(DEV).eval().set_engine(engine)
+    torch.manual_seed(123)
+    out = m(_to_dev(S.make_input('dtu', 32)))
+    assert float(torch.from_numpy(g['out/weights']).sum(1).min()) < 0.1      # the background term is exercised
+    assert max_abs(out['rgb_values'].cpu(), g['out/rgb_values']) < 1e-3
+    hit = torch.from_numpy(g['out/weights']).sum(1, keepdim=True) > 1e-2
+    assert max_abs(out['depth_values'].cpu()[hit], torch.from_numpy(g['out/depth_values'])[hit]) < 1e-3
+
+
+@pytest.mark.parametrize('engine', PARITY_ENGINES)
+def test_reference_train_step_body_replayed_verbatim(engine):
+    """`VolOpt.train_step` (volsdf/vsdf.py:196-219) statement for statement on OUR model class — model(input, fast=1),
+    VolSDFLoss, zero_grad, backward, clip_grad_norm_(1.0), on_after_backward (:454-464), torch.optim.Adam.step — for 3
+    steps, against the same loop on the CPU oracle (fp32, plain autograd, torch.optim.Adam)."""
+    import svolsdf_b200.conf as C
+    from svolsdf_b200.model.loss import VolSDFLoss
+    R, lr = 64, 5e-4
+    model = build_model('dtu', perturb=True, beta=0.05, device=DEV).set_engine(engine)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in state_dict_cpu(model).items()}
+    loss_fn = VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1)
+    loss_fn.iter_step = 0
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    ref_opt = torch.optim.Adam(list(sd.values()), lr=lr)
+    inp_cpu = S.make_input('dtu', R)
+    gt = S.gt_rgb(R)
+    losses, ref_losses = [], []
+
+    def on_after_backward():
+        valid_gradients = True
+        for name, param in model.named_parameters():
+            if param.grad is not None:
+                valid_gradients = not (torch.isnan(param.grad).any() or torch.isinf(param.grad).any())
+                if not valid_gradients:
+                    break
+        if not valid_gradients:
+            optimizer.zero_grad()
+
+    for it in range(3):
+        # ---- the reference's train_step body ----
+        model.train()
+        model_input = {k: v.to(DEV) for k, v in inp_cpu.items()}
+        model_input['iter_step'] = it
+        torch.manual_seed(1000 + it)
+        model_outputs = model(model_input, fast=1)
+        loss_output = loss_fn(model_outputs, {'rgb': gt.to(DEV)})
+        loss = loss_output['loss']
+        optimizer.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        on_after_backward()
+        optimizer.step()
+        losses.append(float(loss))
+        # ---- the same step on the oracle ----
+        torch.manual_seed(1000 + it)
+        o = O.volsdf_forward(sd, C.dtu_model_conf(), inp_cpu, True, fast=1)
+        rl = O.volsdf_loss(o, gt)
+        ref_opt.zero_grad()
+        rl.backward()
+        torch.nn.utils.clip_grad_norm_(list(sd.values()), 1.0)
+        ref_opt.step()
+        ref_losses.append(float(rl))
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
+    # Adam's first updates are ~lr * sign(g): an entry whose near-zero gradient differs in sign moves by up to 2 lr per step
+    for name, p in model.named_parameters():
+        d = (p.detach().cpu() - sd[name].detach()).abs()
+        assert float(d.max()) <= 3 * 2 * lr + 1e-6, name
+        assert float((d > 0.2 * lr).float().mean()) < 0.05, (name, float((d > 0.2 * lr).float().mean()))

@@ -58,3 +58,35 @@ def test_nonfinite_gradients_are_zeroed_but_adam_still_steps():
         for pa, pb in zip(a, b):
             assert torch.isfinite(pb).all()
             assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7)
+
+
+def test_resume_from_a_plain_torch_adam_checkpoint():
+    """The reference saves `torch.optim.Adam(...).state_dict()` (vsdf.py checkpoints): no `capturable`, `step` an int
+    (torch 1.9) or a CPU tensor.  FusedAdam.load_state_dict must turn that into device-resident float32 steps before the
+    kernel sees a pointer (a host pointer used to reach svs_adam_step)."""
+    a, b = _params(5), _params(5)
+    ref = torch.optim.Adam(a, lr=5e-4)
+    g = torch.Generator().manual_seed(6)
+    grads = [[(torch.randn(p.shape, generator=g) * 0.1).to(DEV) for p in a] for _ in range(4)]
+    for it in range(2):
+        for pa, gr in zip(a, grads[it]):
+            pa.grad = gr.clone()
+        ref.step()
+    sd = ref.state_dict()
+    for st in sd['state'].values():            # what torch 1.9 wrote: a Python int
+        st['step'] = int(st['step'])
+    sd['param_groups'][0].pop('capturable', None)
+    with torch.no_grad():
+        for pa, pb in zip(a, b):
+            pb.copy_(pa)
+    fus = FusedAdam(b, lr=5e-4, max_grad_norm=0.0)
+    fus.load_state_dict(sd)
+    assert fus.param_groups[0]['capturable'] is True
+    assert all(s['step'].is_cuda and s['step'].dtype == torch.float32 and float(s['step']) == 2.0 for s in fus.state.values())
+    for it in range(2, 4):
+        for pa, pb, gr in zip(a, b, grads[it]):
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        ref.step()
+        fus.step()
+    for pa, pb in zip(a, b):
+        assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7)
