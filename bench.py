@@ -56,6 +56,8 @@ def parse():
                          'bit-identical per ray to the unsharded one, host work grows with N); local = per-rank streams (data-parallel '
                          'semantics, host work constant); auto = local when N > 1')
     ap.add_argument('--eager', action='store_true', help='issue every step from Python instead of replaying a CUDA graph')
+    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: peer = one kernel over NVLink peer memory (all-reduce + clip + Adam); nccl = NCCL all-reduce + fused step')
     return ap.parse_args()
 
 
@@ -239,8 +241,21 @@ class TrainRig(object):
             model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
         self.model = model
         # clip_grad_norm_(1.0) + NaN guard + Adam of vsdf.py:214-219 as one fused step (svolsdf_b200.optim.FusedAdam)
-        self.opt = opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
-        self.reducer = reducer = sdist.GradAllReducer(model.parameters()) if world > 1 else None
+        # N > 1: the gradient all-reduce is fused into that step — ONE kernel reads every rank's flat gradient buffer over
+        # NVLink peer memory (svs_adam_step_allreduce; --allreduce nccl = round 1's NCCL all-reduce + separate step)
+        self.allreduce = 'none'
+        peer = None
+        if world > 1 and args.allreduce == 'peer':
+            try:
+                peer = sdist.PeerGradBuffer(model.parameters())
+                self.allreduce = 'peer-memory kernel fused with clip+Adam (svs_adam_step_allreduce)'
+            except Exception as e:
+                peer = None
+                self.allreduce = 'nccl (symmetric memory unavailable: %s)' % (str(e).splitlines()[0][:100],)
+        elif world > 1:
+            self.allreduce = 'nccl all-reduce of the flat fp32 gradients + fused clip+Adam'
+        self.opt = opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0, peer=peer)
+        self.reducer = reducer = sdist.GradAllReducer(model.parameters()) if (world > 1 and peer is None) else None
         inp_host = S.make_input(scene, Rg, pixels='perm' if Rg > 4096 else 'random')
         gt_host = S.gt_rgb(Rg)
         lo, hi = sdist.shard_range(Rg, rank, world)
@@ -498,6 +513,7 @@ def run_ours(args):
     rig = TrainRig(args, R, engine, world, rank, dev, W + max(K, n_prof), args.scene)
     Rg = rig.Rg
     step_mode = rig.step_mode
+    allreduce_mode = rig.allreduce
 
     # ---- device-timed region: inputs resident in HBM ----
     for i in range(W):
@@ -596,7 +612,7 @@ def run_ours(args):
         ms_big = timed(lambda i: big.step_device(3 + i), Kl, barrier, max_over_ranks)
         tfl = FLOP_PER_RAY_TRAIN * big.Rg / (ms_big * 1e-3) / 1e12
         large = {'workload': 'BASELINE configs[4]: data-parallel DTU train step, %d rays per GPU = %d rays per step over %d GPU(s), '
-                             'NCCL all-reduce of the flat fp32 gradients inside the graph' % (args.large_rays, big.Rg, world),
+                             'gradient all-reduce: %s' % (args.large_rays, big.Rg, world, big.allreduce),
                  'rays_per_gpu': args.large_rays, 'global_rays': big.Rg, 'value': big.Rg / (ms_big * 1e-3), 'unit': 'rays/s',
                  'ms_per_step': ms_big, 'steps': Kl, 'warmup': 3, 'step_mode': big.step_mode, 'scaling': 'weak',
                  'algorithmic_tflops': tfl, 'algorithmic_frac_of_tensor_peak': tfl / world / pk['tflops_sustained']}
@@ -610,17 +626,15 @@ def run_ours(args):
         frame = frame_leg(args, engine, world, rank, dev, barrier, max_over_ranks)
 
     def leave():
-        """End of a multi-rank run: the NCCL communicator was used inside captured graphs; all graphs are released above,
-        the device is drained and the ranks meet once more before the group is destroyed."""
+        """End of a multi-rank run.  Round 1 left with os._exit because destroy_process_group() blocked forever: the
+        captured CUDA graphs (which hold the NCCL all-reduce nodes) were still alive when the communicator was torn down.
+        Every TrainRig releases its graph before we get here (rig.release()), after which the destructor returns."""
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        if os.environ.get('SVS_BENCH_DESTROY_PG', '0') == '1':
-            dist.destroy_process_group()
-        else:
-            os._exit(0)
+        dist.destroy_process_group()
 
     if rank != 0:
         if world > 1:
@@ -654,7 +668,7 @@ def run_ours(args):
                    'global_rays': Rg, 'parallelism': 'ray-sharded dp%d' % world,
                    'l2': 'per-step working set (~2 GB of saved activation tiles) exceeds the 126 MB L2; no explicit flush',
                    'engine': ENGINE_TEXT[engine][1],
-                   'step_mode': step_mode,
+                   'step_mode': step_mode, 'gradient_allreduce': allreduce_mode,
                    'host_rng': {'single': 'reference order, CPU default generator', 'local': 'per-rank CPU streams (seed + rank)',
                                 'global': 'global-batch draws on every rank, rows sliced (sharded == unsharded per ray)'}[
                                     'single' if world == 1 else ('global' if args.rng == 'global' else 'local')]},

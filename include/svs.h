@@ -26,6 +26,7 @@ extern "C" {
 
 #define SVS_MAX_LAYERS 12
 #define SVS_OPT_MAX_TENSORS 96
+#define SVS_MAX_PEERS 8
 #define SVS_ABI_VERSION 5
 
 typedef enum {
@@ -249,6 +250,20 @@ int svs_density_backward(const float* sdf, int64_t R, int32_t S, const float* be
 int svs_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                   float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
                   float max_norm, int32_t skip_nonfinite, const float* step_count, float* scratch, void* stream);
+
+/* Data-parallel variant ("NCCL allreduce(sum) of one flat fp32 gradient buffer per step ... then grad-clip
+ * and Adam run redundantly on every rank") as ONE kernel over NVLink peer memory: all-reduce(mean) + clip + NaN guard +
+ * Adam.  peer_grads[r] = rank r's flat gradient buffer (n_flat floats, every tensor starting on a multiple of 4 floats, in
+ * the order of `params`), mapped into this process (e.g. torch.distributed._symmetric_memory); peer_flags[r] = rank r's
+ * 2 * SVS_MAX_PEERS uint32 flags (zeroed once, symmetric memory); gmean = local n_flat floats receiving the averaged
+ * gradient; ctrl = 4 + 1024 local uint32 (zeroed once).  All ranks must call it the same number of times.  The launch does not
+ * return before every peer has read this rank's buffer, so later work on the stream may overwrite it.  world == 1: plain
+ * clip + Adam from peer_grads[0]. */
+int svs_adam_step_allreduce(int32_t n_tensors, float* const* params, float* const* exp_avg, float* const* exp_avg_sq,
+                            const int64_t* numel, int32_t world, int32_t rank, const float* const* peer_grads,
+                            uint32_t* const* peer_flags, int64_t n_flat, float* gmean, float lr, float beta1, float beta2,
+                            float eps, float max_norm, int32_t skip_nonfinite, const float* step_count, float* scratch,
+                            uint32_t* ctrl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * MVS cost lookup of the reference's training loop — VolOpt.cost_mapping (volsdf/vsdf.py:382-452).

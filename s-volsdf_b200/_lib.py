@@ -87,6 +87,7 @@ SIGNATURES = {
     'svs_composite_backward': (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     'svs_density_forward': (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _P, _P]),
     'svs_adam_step': (C.c_int, [_I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I32, _P, _P, _P]),
+    'svs_adam_step_allreduce': (C.c_int, [_I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P]),
     'svs_density_backward': (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _P, _P, _P, _P]),
     'svs_cost_mapping': (C.c_int, [_P, _I64, _I32, C.POINTER(MvsView), _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
 }

@@ -82,6 +82,156 @@ adam_kernel(const OptTensors t, const float* __restrict__ scratch, const float* 
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Data-parallel step as ONE kernel over NVLink peer memory: all-reduce(mean) of the flat gradient buffer + global-norm
+// clipping + non-finite guard + Adam.  Every rank keeps its gradients in a symmetric (peer-mapped) flat buffer; the
+// kernel (a) meets the other ranks on flags in peer memory (their backward has finished), (b) reads element i from all
+// `world` buffers in rank order — the same order on every rank, so the replicas stay bit-identical — and keeps the mean
+// in a local buffer while accumulating sum g^2 / the non-finite flag, (c) crosses a grid barrier, (d) runs Adam from the
+// local mean, (e) waits until every peer has finished reading this rank's buffer before the stream may overwrite it.
+// One-shot reads: 3.2 MB x world per rank, latency-bound like the NCCL all-reduce it replaces, but without the copy-in /
+// copy-out / divide / separate norm and Adam launches around it.  One block per SM (all co-resident: the barriers spin).
+// ----------------------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+  const float* grad[SVS_MAX_PEERS];   // flat gradient buffer of every rank (peer-mapped device pointers)
+  uint32_t* flag[SVS_MAX_PEERS];      // 2 * SVS_MAX_PEERS uint32 flags of every rank
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ctrl (local, zero-initialised once, 4 + gridDim words): [1] go flag, [2] grid-barrier arrivals, [3] completed launches,
+// [4 ...] per-block partial sums of squares
+__global__ void __launch_bounds__(512, 1)
+allreduce_adam_kernel(const OptTensors t, const PeerPtrs peers, int world, int rank, long long n_flat, float* __restrict__ gmean,
+                      float* __restrict__ scratch, uint32_t* __restrict__ ctrl, const float* __restrict__ step_count, float lr,
+                      float beta1, float beta2, float eps, float max_norm, int skip_nonfinite) {
+  __shared__ float red[16];
+  __shared__ int redbad;
+  const int tid = threadIdx.x;
+  // ctrl[3] = number of completed launches: stable until block 0 bumps it at the very end, after the grid barrier that
+  // every block passes only after this read
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(ctrl + 3) + 1;
+  // ---- (a) cross-GPU barrier: every rank's gradients are complete ----
+  if (blockIdx.x == 0) {
+    if (tid == 0) {
+      scratch[0] = 0.f;
+      scratch[1] = 0.f;
+    }
+    if (world > 1 && tid < world) {
+      __threadfence_system();
+      st_release_sys(peers.flag[tid] + rank, epoch);
+      while (ld_acquire_sys(peers.flag[rank] + tid) < epoch) {}
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(ctrl + 1, epoch);
+    }
+  } else {
+    if (tid == 0)
+      while (ld_acquire_gpu(ctrl + 1) < epoch) {}
+    __syncthreads();
+  }
+  // ---- (b) mean over the ranks, norm, non-finite flag ----
+  const float inv_w = 1.0f / (float)world;
+  float ss = 0.f;
+  bool bad = false;
+  const long long n4 = n_flat >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 g = __ldcg(reinterpret_cast<const float4*>(peers.grad[r]) + i);
+      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+    }
+    a.x *= inv_w; a.y *= inv_w; a.z *= inv_w; a.w *= inv_w;
+    reinterpret_cast<float4*>(gmean)[i] = a;
+    bad |= !(isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w));
+    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+  }
+  ss = warp_sum(ss);
+  bad = __any_sync(0xffffffffu, bad);
+  if (tid == 0) redbad = 0;
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    red[tid >> 5] = ss;
+    if (bad) redbad = 1;
+  }
+  __syncthreads();
+  float* partial = reinterpret_cast<float*>(ctrl + 4);   // one sum of squares per block: summed in a FIXED order below, so
+  if (tid == 0) {                                        // every rank clips by the bit-identical norm (replicas stay equal)
+    float tot = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+    partial[blockIdx.x] = tot;
+    if (redbad) scratch[1] = 1.f;
+    // ---- (c) grid barrier (all blocks resident) ----
+    __threadfence();
+    atomicAdd(ctrl + 2, 1u);
+    const uint32_t target = epoch * gridDim.x;
+    while (ld_acquire_gpu(ctrl + 2) < target) {}
+  }
+  __syncthreads();
+  // this rank is done with the peers' buffers
+  if (blockIdx.x == 0 && world > 1 && tid < world) st_release_sys(peers.flag[tid] + SVS_MAX_PEERS + rank, epoch);
+  // ---- (d) Adam from the local mean ----
+  if (tid < 32) {
+    float tot = 0.f;
+    for (int i = tid; i < (int)gridDim.x; i += 32) tot += __ldcg(partial + i);
+    tot = warp_sum(tot);
+    if (tid == 0) {
+      red[0] = tot;
+      if (blockIdx.x == 0) scratch[0] = tot;
+    }
+  }
+  __syncthreads();
+  const volatile float* vs = scratch;
+  const bool nonfinite = skip_nonfinite && vs[1] != 0.f;
+  float clip = 1.0f;
+  if (max_norm > 0.f) clip = fminf(max_norm / (sqrtf(red[0]) + 1e-6f), 1.0f);
+  const float step = *step_count;
+  const float bc1 = 1.0f - powf(beta1, step), bc2 = 1.0f - powf(beta2, step);
+  const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  long long off = 0;
+  for (int ti = 0; ti < t.count; ++ti) {
+    const long long n = t.n[ti];
+    float* p = t.p[ti];
+    float* m = t.m[ti];
+    float* v = t.v[ti];
+    const float* g = gmean + off;
+    for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const float gi = nonfinite ? 0.f : g[i] * clip;
+      const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+      const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+    off += (n + 3) & ~3LL;   // every tensor starts on a 16-byte boundary of the flat buffer
+  }
+  // ---- (e) nobody may overwrite its gradients before all peers have read them ----
+  if (blockIdx.x == 0) {
+    if (world > 1 && tid < world)
+      while (ld_acquire_sys(peers.flag[rank] + SVS_MAX_PEERS + tid) < epoch) {}
+    __syncthreads();
+    if (tid == 0) ctrl[3] = epoch;
+  }
+}
+
 }  // namespace svs
 
 using namespace svs;
@@ -109,6 +259,47 @@ extern "C" int svs_adam_step(int32_t n_tensors, float* const* params, const floa
   grad_norm_kernel<<<grid, kOptBlock, 0, st>>>(t, scratch);
   SVS_LAUNCH_OK();
   adam_kernel<<<grid, kOptBlock, 0, st>>>(t, scratch, step_count, lr, beta1, beta2, eps, max_norm, skip_nonfinite);
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
+
+extern "C" int svs_adam_step_allreduce(int32_t n_tensors, float* const* params, float* const* exp_avg, float* const* exp_avg_sq,
+                                       const int64_t* numel, int32_t world, int32_t rank, const float* const* peer_grads,
+                                       uint32_t* const* peer_flags, int64_t n_flat, float* gmean, float lr, float beta1,
+                                       float beta2, float eps, float max_norm, int32_t skip_nonfinite, const float* step_count,
+                                       float* scratch, uint32_t* ctrl, void* stream) {
+  SVS_CHECK_ARG(n_tensors > 0 && n_tensors <= SVS_OPT_MAX_TENSORS, "svs_adam_step_allreduce: %d tensors (max %d)", n_tensors,
+                SVS_OPT_MAX_TENSORS);
+  SVS_CHECK_ARG(world >= 1 && world <= SVS_MAX_PEERS && rank >= 0 && rank < world, "svs_adam_step_allreduce: world %d rank %d", world, rank);
+  SVS_CHECK_ARG(params && exp_avg && exp_avg_sq && numel && peer_grads && gmean && step_count && scratch && ctrl && (world == 1 || peer_flags),
+                "svs_adam_step_allreduce: null pointer");
+  SVS_CHECK_ARG(n_flat > 0 && (n_flat & 3) == 0, "svs_adam_step_allreduce: flat size must be a positive multiple of 4");
+  OptTensors t;
+  memset(&t, 0, sizeof(t));
+  t.count = n_tensors;
+  int64_t need = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    SVS_CHECK_ARG(params[i] && exp_avg[i] && exp_avg_sq[i] && numel[i] >= 0, "svs_adam_step_allreduce: tensor %d", i);
+    t.p[i] = params[i]; t.m[i] = exp_avg[i]; t.v[i] = exp_avg_sq[i]; t.n[i] = numel[i];
+    need += (numel[i] + 3) & ~(int64_t)3;
+  }
+  SVS_CHECK_ARG(need == n_flat, "svs_adam_step_allreduce: flat buffer holds %lld floats, the tensors need %lld", (long long)n_flat, (long long)need);
+  PeerPtrs pp;
+  memset(&pp, 0, sizeof(pp));
+  for (int r = 0; r < world; ++r) {
+    SVS_CHECK_ARG(peer_grads[r] && (world == 1 || peer_flags[r]), "svs_adam_step_allreduce: peer %d", r);
+    pp.grad[r] = peer_grads[r];
+    pp.flag[r] = world > 1 ? peer_flags[r] : nullptr;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = kNumSMs;
+  }
+  allreduce_adam_kernel<<<n_sm, 512, 0, (cudaStream_t)stream>>>(t, pp, world, rank, n_flat, gmean, scratch, ctrl, step_count, lr,
+                                                               beta1, beta2, eps, max_norm, skip_nonfinite);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

@@ -90,6 +90,64 @@ class GradAllReducer(object):
         return self.flat
 
 
+class PeerGradBuffer(object):
+    """The flat gradient buffer of `GradAllReducer` placed in SYMMETRIC memory (torch.distributed._symmetric_memory: every
+    rank's allocation is mapped into every other rank's address space over NVLink) plus the flag words of the device-side
+    barrier.  `FusedAdam(..., peer=PeerGradBuffer(params))` then replaces [copy-in, NCCL all-reduce, divide, copy-out, norm
+    launch, Adam launch] by [copy-in, ONE kernel] (`svs_adam_step_allreduce`, csrc/optim.cu): the kernel reads the
+    gradients of all ranks straight from peer memory.  world == 1: ordinary device memory, same kernel."""
+
+    MAX_PEERS = 8
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        if self.world > self.MAX_PEERS:
+            raise ValueError('PeerGradBuffer supports up to %d ranks of one NVLink domain' % self.MAX_PEERS)
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4        # every tensor starts on a 16-byte boundary (float4 loads over NVLink)
+        self.n_flat = off
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            name = pg.group_name
+            if hasattr(symm, 'enable_symm_mem_for_group'):
+                try:
+                    symm.enable_symm_mem_for_group(name)
+                except Exception:
+                    pass
+            self.flat = symm.empty(self.n_flat, dtype=torch.float32, device=dev)
+            self.flags = symm.empty(2 * self.MAX_PEERS, dtype=torch.int32, device=dev)
+            self.flat.zero_()
+            self.flags.zero_()
+            self._h_flat = symm.rendezvous(self.flat, name)
+            self._h_flags = symm.rendezvous(self.flags, name)
+            self.peer_grads = [int(x) for x in self._h_flat.buffer_ptrs]
+            self.peer_flags = [int(x) for x in self._h_flags.buffer_ptrs]
+            torch.cuda.synchronize()
+            dist.barrier(group)                     # nobody signals before every flag word is zero
+        else:
+            self.flat = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
+            self.flags = None
+            self.peer_grads, self.peer_flags = [self.flat.data_ptr()], None
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.gmean = torch.zeros(self.n_flat, dtype=torch.float32, device=dev)
+        self.mean_views = [self.gmean[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.ctrl = torch.zeros(4 + 1024, dtype=torch.int32, device=dev)   # barrier words + per-block partial norms
+
+    def nbytes(self):
+        return self.n_flat * 4
+
+    def load_grads(self):
+        """this rank's gradients -> the symmetric buffer (one multi-tensor copy)"""
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch._foreach_copy_(self.views, grads)
+
+
 def all_converged(flag, group=None):
     """Optional batch-global convergence (ray_sampler.py:136) across ranks: max of the per-rank flags."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -72,7 +72,8 @@ def test_resume_from_a_plain_torch_adam_checkpoint():
         for pa, gr in zip(a, grads[it]):
             pa.grad = gr.clone()
         ref.step()
-    sd = ref.state_dict()
+    import copy
+    sd = copy.deepcopy(ref.state_dict())      # (state_dict() hands out the live per-parameter dicts)
     for st in sd['state'].values():            # what torch 1.9 wrote: a Python int
         st['step'] = int(st['step'])
     sd['param_groups'][0].pop('capturable', None)
@@ -90,3 +91,27 @@ def test_resume_from_a_plain_torch_adam_checkpoint():
         fus.step()
     for pa, pb in zip(a, b):
         assert torch.allclose(pa, pb, rtol=1e-5, atol=2e-7)
+
+
+def test_peer_allreduce_step_equals_the_two_launch_step_on_one_gpu():
+    """svs_adam_step_allreduce with world = 1 (the multi-GPU kernel reading its own buffer) == svs_adam_step; the N > 1
+    path is exercised by tools/peer_adam_check.py under torchrun (replicas bit-identical, == NCCL all-reduce + step)."""
+    from svolsdf_b200.dist import PeerGradBuffer
+    a, b = _params(8), _params(8)
+    ref = FusedAdam(a, lr=5e-4, max_grad_norm=1.0)
+    peer = PeerGradBuffer(b)
+    assert peer.world == 1 and peer.n_flat % 4 == 0 and all(o % 4 == 0 for o in peer.offsets)
+    fus = FusedAdam(b, lr=5e-4, max_grad_norm=1.0, peer=peer)
+    g = torch.Generator().manual_seed(9)
+    for it in range(5):
+        scale = 10.0 if it % 2 == 0 else 1e-3
+        for pa, pb in zip(a, b):
+            gr = (torch.randn(pa.shape, generator=g) * scale).to(DEV)
+            if it == 3 and pa.dim() == 2 and pa.shape[0] == 217:
+                gr[5, 7] = float('inf')
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        ref.step()
+        fus.step()
+        for pa, pb in zip(a, b):
+            assert torch.isfinite(pb).all()
+            assert torch.allclose(pa, pb, rtol=1e-5, atol=3e-7), it
