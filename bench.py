@@ -45,7 +45,7 @@ def parse():
     ap.add_argument('--group', type=int, default=512, help='frame: rays per sampler convergence group (eval_vsdf.py: 512)')
     ap.add_argument('--large-rays', type=int, default=8192, help='large_batch leg: rays per GPU (8 GPUs: 65536 per step)')
     ap.add_argument('--ref-rays', type=int, default=None, help='--impl reference: rays per step (default: --rays, the same config)')
-    ap.add_argument('--skip', default='', help='comma list of legs to skip: frame,large,parity,gpu_eager,engines')
+    ap.add_argument('--skip', default='', help='comma list of legs to skip: frame,large,parity,gpu_eager,engines,mvs')
     ap.add_argument('--chunk', type=int, default=16384, help='frame workload: rays per model call (= sampler convergence group)')
     ap.add_argument('--beta', type=float, default=None, help='frame workload: density.beta override (0.01 = trained-like, 5 sampler iterations)')
     ap.add_argument('--scene', default='dtu', choices=['dtu', 'bmvs'],
@@ -473,6 +473,54 @@ def frame_leg(args, engine, world, rank, dev, barrier, max_over_ranks):
             'rgb_mean': float(out['rgb_values'].mean()), 'depth_mean': float(out['depth_values'].mean())}
 
 
+def mvs_leg(args, engine, dev, R, K):
+    """the paper configuration's step (use_mvs: vsdf.py:205-211; loss.py:80-115 with mvs / sparsity terms):
+    forward + CostMapper over 3 source views (48 x 288 x 384 probability volumes) + VolSDFLoss + backward + clip + Adam as
+    one CUDA graph."""
+    import svolsdf_b200.conf as C
+    import svolsdf_b200.scene as S
+    from svolsdf_b200.model.loss import VolSDFLoss
+    from svolsdf_b200.model.network import VolSDFNetwork
+    from svolsdf_b200.model.ray_sampler import RefRng, TapeRng
+    from svolsdf_b200.mvs import CostMapper
+    from svolsdf_b200.optim import FusedAdam
+    from svolsdf_b200.train import GraphedTrainStep
+    torch.manual_seed(0)
+    model = VolSDFNetwork(C.dtu_model_conf()).to(dev).train().set_engine(engine)
+    opt = FusedAdam(model.parameters(), lr=5e-4, max_grad_norm=1.0)
+    inp = {k: v.to(dev) for k, v in S.make_input('dtu', R).items()}
+    gt = {'rgb': S.gt_rgb(R).to(dev), 'rgb_smooth': S.gt_rgb(R, seed=5).to(dev)}
+    views = S.mvs_views(n_views=3, dz=48, h=288, w=384, img_res=(1200, 1600), seed=9)
+    ids = [25, 22, 28]
+    cm = CostMapper([v['cost'][None] for v in views], [v['z_mvs'][None] for v in views], [v['K'] for v in views],
+                    [v['c2w'] for v in views], ids, (1200, 1600), inverse_depth=True)
+    loss_fn = VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=1.0, sparse_weight=1.0, anneal_rgb=200, gce=0.5)
+    step = GraphedTrainStep(model, opt, loss_fn, inp, gt, grad_clip=0.0, cost_mapper=cm, own_view=ids[1])
+    torch.manual_seed(77)
+    tapes = []
+    for _ in range(3 + K):
+        tr = TapeRng(RefRng(dev))
+        model.rng_source = tr
+        with torch.no_grad():
+            model(inp, fast=1)
+        tapes.append(tr.tape)
+    model.rng_source = step.rng
+    for i in range(3):
+        step(draws=tapes[i], own_view=ids[i % 3])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(draws=tapes[3 + i], own_view=ids[i % 3])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    return {'workload': 'MVS-supervised DTU train step (paper configuration, SURVEY.md 8f-1): forward + cost lookup in 3 source views '
+                        '(48x288x384 volumes) + VolSDFLoss (L1 + eikonal + GCE(0.5) on the weights + annealed sparsity) + backward '
+                        '+ clip + Adam, one CUDA graph', 'rays': R, 'value': R / (ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms,
+            'steps': K, 'warmup': 3, 'loss': float(step.loss)}
+
+
 MLP_KERNELS = ('mlp_',)
 
 
@@ -640,7 +688,12 @@ def run_ours(args):
         if world > 1:
             leave()
         return
-    cpu = parity = gpu_eager = None
+    cpu = parity = gpu_eager = mvs = None
+    if world == 1 and 'mvs' not in skip and not bmvs:
+        try:
+            mvs = mvs_leg(args, engine, dev, R, max(3, min(K, 10)))
+        except Exception as e:
+            mvs = {'error': str(e).splitlines()[0][:200]}
     if world == 1:
         if not args.no_cpu_baseline:
             cpu = cpu_train_steps(args.cpu_rays, 2, 1)
@@ -676,7 +729,7 @@ def run_ours(args):
                 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
         'algorithmic_tflops': step_tflops, 'algorithmic_frac_of_tensor_peak': step_tflops * 1.0 / world / pk['tflops_sustained'],
-        'parity': parity, 'gpu_eager_baseline': gpu_eager, 'frame': frame, 'large_batch': large,
+        'parity': parity, 'gpu_eager_baseline': gpu_eager, 'frame': frame, 'large_batch': large, 'mvs_step': mvs,
         'kernels': kernels, 'rooflines': rooflines, 'other_engines': other,
     }
     print(json.dumps(line))

@@ -282,11 +282,14 @@ typedef struct svs_mvs_view {
   int32_t Dz, H, W;
   float fx, fy, cx, cy, sk; /* K[0,0], K[1,1], K[0,2], K[1,2], K[0,1] of the view (vsdf.py:398-399) */
   float c2w[12];            /* rows 0..2 of the camera-to-world pose, row-major (vsdf.py:396-397) */
-  int32_t same_view;        /* 1: the batch's own image (ts[0] == id_k, vsdf.py:392) */
+  int32_t same_view;        /* 1: the batch's own image (ts[0] == id_k, vsdf.py:392); used when own_view == NULL */
+  int32_t view_id;          /* id_k of the view (self.trains_i[i]); compared with *own_view when that is given */
 } svs_mvs_view;
+/* own_view: optional DEVICE int32 holding the batch's image index ts[0]; when non-NULL the own view is decided on the
+ * device (view_id == *own_view), so the call can sit inside a CUDA graph whose replays change the batch image. */
 int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views,
-                     int32_t img_h, int32_t img_w, int32_t inverse_depth, float* cost_j, float* cost_mvs,
-                     uint8_t* valid, void* stream);
+                     int32_t img_h, int32_t img_w, int32_t inverse_depth, const int32_t* own_view, float* cost_j,
+                     float* cost_mvs, uint8_t* valid, void* stream);
 
 #ifdef __cplusplus
 }

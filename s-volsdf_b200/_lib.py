@@ -46,7 +46,7 @@ class MvsView(C.Structure):
     _fields_ = [('cost', C.c_void_p), ('z_near', C.c_void_p), ('z_far', C.c_void_p),
                 ('Dz', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('fx', C.c_float), ('fy', C.c_float), ('cx', C.c_float), ('cy', C.c_float), ('sk', C.c_float),
-                ('c2w', C.c_float * 12), ('same_view', C.c_int32)]
+                ('c2w', C.c_float * 12), ('same_view', C.c_int32), ('view_id', C.c_int32)]
 
 
 _P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
@@ -89,7 +89,7 @@ SIGNATURES = {
     'svs_adam_step': (C.c_int, [_I32, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I32, _P, _P, _P]),
     'svs_adam_step_allreduce': (C.c_int, [_I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P]),
     'svs_density_backward': (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _P, _P, _P, _P]),
-    'svs_cost_mapping': (C.c_int, [_P, _I64, _I32, C.POINTER(MvsView), _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    'svs_cost_mapping': (C.c_int, [_P, _I64, _I32, C.POINTER(MvsView), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -62,12 +62,13 @@ __device__ __forceinline__ float trilinear(const float* __restrict__ vol, int Dz
 
 __global__ void __launch_bounds__(256)
 cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, float half_w, float half_h, int inverse_depth,
-                    float* __restrict__ cost_j, float* __restrict__ cost_mvs, uint8_t* __restrict__ valid) {
+                    const int32_t* __restrict__ own_view, float* __restrict__ cost_j, float* __restrict__ cost_mvs, uint8_t* __restrict__ valid) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
   float sum = 0.f, own = 0.f;
   bool ok = false;
+  const int own_id = own_view ? __ldg(own_view) : 0;
   for (int k = 0; k < a.n_views; ++k) {
     const svs_mvs_view& v = a.v[k];
     // world -> camera: (p - t) @ R, R = c2w[:, :3]                                       vsdf.py:401-402
@@ -93,7 +94,7 @@ cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, f
     }
     const bool bad2 = (near < 1e-5f) || (far < 1e-5f) || (zn > 1.01f) || (zn < -1.01f) || bad;   // :434
     const float c = bad2 ? 0.f : trilinear(v.cost, v.Dz, v.H, v.W, x, y, zn);           // :435-440 (-99 -> all padding)
-    if (v.same_view) {
+    if (own_view ? (v.view_id == own_id) : (v.same_view != 0)) {
       own = c;                                                                          // :443-444
     } else {
       sum += c;                                                                         // :446-448
@@ -110,8 +111,8 @@ cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, f
 using namespace svs;
 
 extern "C" int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views,
-                                int32_t img_h, int32_t img_w, int32_t inverse_depth, float* cost_j, float* cost_mvs,
-                                uint8_t* valid, void* stream) {
+                                int32_t img_h, int32_t img_w, int32_t inverse_depth, const int32_t* own_view, float* cost_j,
+                                float* cost_mvs, uint8_t* valid, void* stream) {
   SVS_CHECK_ARG(N >= 0 && D >= 1, "svs_cost_mapping: need N >= 0, D >= 1");
   SVS_CHECK_ARG(xyz && cost_j && cost_mvs && valid && views, "svs_cost_mapping: null pointer");
   SVS_CHECK_ARG(n_views >= 1 && n_views <= kMaxMvsViews, "svs_cost_mapping: 1 <= n_views <= %d (got %d)", kMaxMvsViews, n_views);
@@ -131,7 +132,7 @@ extern "C" int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const sv
   ProfScope ps("cost_mapping", 0.0, (double)n * (12.0 + 9.0 + 64.0 * n_views), st);
   // (_w - 1) / 2 and (_h - 1) / 2 are Python floats in the reference; the tensor is divided by their fp32 value
   const float half_w = (float)((double)(img_w - 1) / 2.0), half_h = (float)((double)(img_h - 1) / 2.0);
-  cost_mapping_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, xyz, n, half_w, half_h, inverse_depth, cost_j, cost_mvs, valid);
+  cost_mapping_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, xyz, n, half_w, half_h, inverse_depth, own_view, cost_j, cost_mvs, valid);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

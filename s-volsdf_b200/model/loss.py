@@ -66,6 +66,33 @@ class VolSDFLoss(nn.Module):
         return ((1. / (model_outputs[key].squeeze() + 1e-3)) * (conf_ray < self.confi)).mean()
 
     # ---- total ---------------------------------------------------------------------------------------
+    def forward_device(self, model_outputs, ground_truth, iter_step):
+        """forward() with the iteration counter as a DEVICE scalar and no host-side branch on it: the annealing switch
+        (`iter_step < anneal_rgb`, loss.py:99-108) becomes a blend of both photometric terms, so the whole loss can be
+        captured in a CUDA graph and replayed across the switch (svolsdf_b200.train.GraphedTrainStep increments the
+        counter inside the graph).  Same values as forward() for every iteration."""
+        dev = model_outputs['rgb_values'].device
+        zero = torch.zeros((), device=dev)
+        has_mvs = 'pi' in model_outputs
+        out = {
+            'rgb_loss': self.get_rgb_loss(model_outputs['rgb_values'], ground_truth['rgb'].to(dev)),
+            'eikonal_loss': self.get_eikonal_loss(model_outputs['grad_theta']) if 'grad_theta' in model_outputs else zero,
+            'mvs_loss': self.get_mvs_loss(model_outputs) if has_mvs and self.mvs_weight > 0 else zero,
+            'sparse_loss': zero,
+        }
+        sparse_term = zero
+        if has_mvs and self.sparse_weight > 0 and self.anneal_rgb > 0:
+            it = iter_step.to(torch.float32)
+            ann = (it < self.anneal_rgb).to(torch.float32)
+            smooth = self.get_rgb_loss(model_outputs['rgb_values'], ground_truth['rgb_smooth'].to(dev), model_outputs, t=1e-8)
+            out['rgb_loss'] = ann * smooth + (1.0 - ann) * out['rgb_loss']
+            out['sparse_loss'] = ann * self.get_sparse_loss(model_outputs)
+            anneal_sparse = ann * (1.0 - (it / self.anneal_rgb).clamp(0.0, 1.0))
+            sparse_term = self.sparse_weight * anneal_sparse * out['sparse_loss']
+        out['loss'] = self.rgb_weight * out['rgb_loss'] + self.eikonal_weight * out['eikonal_loss'] + \
+            self.mvs_weight * out['mvs_loss'] + sparse_term
+        return out
+
     def forward(self, model_outputs, ground_truth):
         dev = model_outputs['rgb_values'].device
         zero = torch.zeros((), device=dev)

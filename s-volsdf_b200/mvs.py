@@ -50,15 +50,19 @@ class CostMapper(object):
         (`ts[0] == id_k` marks the batch's own view, vsdf.py:392); xyz_raw (N, D, 3) world points."""
         xyz = xyz_raw.detach().float().contiguous()
         N, D = int(xyz.shape[0]), int(xyz.shape[1])
-        own = int(ts[0]) if torch.is_tensor(ts) else int(ts)
+        # a CUDA int32 tensor keeps the choice of the own view on the device (CUDA-graph replays with changing batches,
+        # svolsdf_b200.train.GraphedTrainStep); anything else is read on the host like the reference's `ts[0] == id_k`
+        own_dev = ts if (torch.is_tensor(ts) and ts.is_cuda and ts.dtype == torch.int32) else None
+        own = -1 if own_dev is not None else (int(ts[0]) if torch.is_tensor(ts) else int(ts))
         arr = (L.MvsView * len(self._desc))()
         for i, v in enumerate(self._desc):
             arr[i] = v
+            arr[i].view_id = self.view_ids[i]
             arr[i].same_view = 1 if self.view_ids[i] == own else 0
         dev = xyz.device
         cost_j = torch.empty(N, D, dtype=torch.float32, device=dev)
         cost_mvs = torch.empty(N, D, dtype=torch.float32, device=dev)
         valid = torch.empty(N, D, dtype=torch.uint8, device=dev)
         L.call('svs_cost_mapping', L.ptr(xyz), N, D, arr, len(self._desc), self.img_res[0], self.img_res[1],
-               1 if self.inverse_depth else 0, L.ptr(cost_j), L.ptr(cost_mvs), L.ptr(valid), L.stream())
+               1 if self.inverse_depth else 0, L.ptr(own_dev), L.ptr(cost_j), L.ptr(cost_mvs), L.ptr(valid), L.stream())
         return cost_j, cost_mvs, valid.bool()

@@ -31,17 +31,35 @@ def default_loss(out, gt):
 
 
 class GraphedTrainStep(object):
+    """loss_fn: either `f(model_outputs, gt) -> scalar` (rgb + eikonal, the default), or a `VolSDFLoss` module — then the
+    step is the MVS-supervised one of the paper configuration (vsdf.py:205-211 with `use_mvs`): `cost_mapper` (a
+    svolsdf_b200.mvs.CostMapper) looks up p_j / p_i for the step's samples inside the graph, `example_gt` is the
+    reference's ground-truth dict ({'rgb', 'rgb_smooth'}), the batch's image index lives in `self.own_view` (device int32)
+    and the iteration counter that drives the annealing in `self.iter_step` (device float, incremented by the graph).
+    Optimizers other than FusedAdam get no NaN guard inside the graph (on_after_backward needs a host sync)."""
+
     def __init__(self, model, optimizer, loss_fn=default_loss, example_input=None, example_gt=None, grad_clip=1.0,
-                 reducer=None, world=1, make_rng=None, warmup=3):
+                 reducer=None, world=1, make_rng=None, warmup=3, cost_mapper=None, own_view=0, iter_step=0):
         assert example_input is not None and example_gt is not None
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.grad_clip, self.reducer, self.world = grad_clip, reducer, world
-        dev = example_gt.device
+        self.cost_mapper = cost_mapper
+        self.module_loss = hasattr(loss_fn, 'forward_device')
+        if getattr(loss_fn, 'iter_step', None) is not None and not self.module_loss:
+            raise ValueError('loss modules with a host-side step counter cannot be captured (their annealing would freeze); '
+                             'pass svolsdf_b200.model.loss.VolSDFLoss or a stateless function')
+        if isinstance(example_gt, dict):
+            dev = next(iter(example_gt.values())).device
+        else:
+            dev = example_gt.device
         self.device = dev
         self.make_rng = make_rng or (lambda: RefRng(dev))
         # static inputs
         self.inp = {k: v.detach().clone() for k, v in example_input.items() if torch.is_tensor(v)}
-        self.gt = example_gt.detach().clone()
+        self.gt = ({k: v.detach().clone() for k, v in example_gt.items()} if isinstance(example_gt, dict)
+                   else example_gt.detach().clone())
+        self.own_view = torch.tensor([int(own_view)], dtype=torch.int32, device=dev)
+        self.iter_step = torch.tensor(float(iter_step), dtype=torch.float32, device=dev)
         # one eager dry run records which random tensors a step draws (shapes / order of the reference)
         tape = TapeRng(self.make_rng())
         model.rng_source = tape
@@ -54,6 +72,7 @@ class GraphedTrainStep(object):
 
         # warm-up + capture run real optimisation steps: remember parameters / optimizer state and put them back
         # afterwards (in place, the graph holds their addresses)
+        saved_iter = self.iter_step.clone()
         saved_params = [p.detach().clone() for p in model.parameters()]
         saved_state = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()}
                        for p in model.parameters()]
@@ -75,12 +94,19 @@ class GraphedTrainStep(object):
                 for k, v in self.opt.state.get(p, {}).items():
                     if torch.is_tensor(v):
                         v.copy_(st[k]) if k in st else v.zero_()
+            self.iter_step.copy_(saved_iter)
         torch.cuda.synchronize()
 
     def _body(self):
         self.rng.rewind()
         out = self.model(self.inp, fast=1)
-        loss = self.loss_fn(out, self.gt)
+        if self.cost_mapper is not None:   # vsdf.py:207-209
+            out['pj'], out['pi'], _ = self.cost_mapper(out['depth_vals'], self.own_view, out['xyz'])
+        if self.module_loss:
+            loss = self.loss_fn.forward_device(out, self.gt, self.iter_step)['loss']
+            self.iter_step.add_(1.0)
+        else:
+            loss = self.loss_fn(out, self.gt)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         if self.reducer is not None:
@@ -101,12 +127,18 @@ class GraphedTrainStep(object):
         for dst, src in zip(self.rng.tape, tape):
             dst.copy_(src, non_blocking=True)
 
-    def __call__(self, model_input=None, gt=None, draws=None):
+    def __call__(self, model_input=None, gt=None, draws=None, own_view=None):
         if model_input is not None:
             for k, v in self.inp.items():
                 v.copy_(model_input[k], non_blocking=True)
         if gt is not None:
-            self.gt.copy_(gt, non_blocking=True)
+            if isinstance(self.gt, dict):
+                for k, v in self.gt.items():
+                    v.copy_(gt[k], non_blocking=True)
+            else:
+                self.gt.copy_(gt, non_blocking=True)
+        if own_view is not None:
+            self.own_view.fill_(int(own_view))
         if draws is not None:
             self.load_draws(draws)
         self.graph.replay()

@@ -75,12 +75,12 @@ def test_argument_validation_and_empty_inputs_need_no_gpu():
     v = (L.MvsView * 9)()
     for i in range(9):
         v[i].cost, v[i].z_near, v[i].z_far, v[i].Dz, v[i].H, v[i].W = 4096, 4096, 4096, 4, 6, 8
-    assert lib.svs_cost_mapping(p, 0, 20, v, 3, 72, 96, 1, p, p, p, None) == 0          # no samples
-    assert lib.svs_cost_mapping(p, 4, 20, v, 9, 72, 96, 1, p, p, p, None) < 0           # > 8 views
+    assert lib.svs_cost_mapping(p, 0, 20, v, 3, 72, 96, 1, None, p, p, p, None) == 0          # no samples
+    assert lib.svs_cost_mapping(p, 4, 20, v, 9, 72, 96, 1, None, p, p, p, None) < 0           # > 8 views
     assert b'n_views' in lib.svs_last_error()
-    assert lib.svs_cost_mapping(p, 4, 20, v, 0, 72, 96, 1, p, p, p, None) < 0
-    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 1, 96, 1, p, p, p, None) < 0            # degenerate image
+    assert lib.svs_cost_mapping(p, 4, 20, v, 0, 72, 96, 1, None, p, p, p, None) < 0
+    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 1, 96, 1, None, p, p, p, None) < 0            # degenerate image
     v[1].cost = None
-    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 72, 96, 1, p, p, p, None) < 0
+    assert lib.svs_cost_mapping(p, 4, 20, v, 3, 72, 96, 1, None, p, p, p, None) < 0
     assert b'view 1' in lib.svs_last_error()
-    assert lib.svs_cost_mapping(None, 4, 20, v, 3, 72, 96, 1, p, p, p, None) < 0
+    assert lib.svs_cost_mapping(None, 4, 20, v, 3, 72, 96, 1, None, p, p, p, None) < 0

@@ -356,3 +356,16 @@ def test_cost_mapping_rejects_bad_arguments():
     ids, cm = _mapper(views, (1, 16), True)
     with pytest.raises(L.SvsError):
         cm(torch.zeros(2, 2, device=DEV), torch.tensor([0]), torch.zeros(2, 2, 3, device=DEV))
+
+
+def test_cost_mapping_own_view_on_the_device():
+    """`ts` as a CUDA int32 tensor: the own view is chosen inside the kernel (CUDA-graph replays) — same results"""
+    views = S.mvs_views(n_views=3, dz=48, h=72, w=96, img_res=(288, 384), seed=9)
+    xyz = S.mvs_points(300, 40, seed=11).to(DEV)
+    ids, cm = _mapper(views, (288, 384), True)
+    z = torch.zeros(300, 40, device=DEV)
+    for own in (ids[0], ids[2], 999):
+        a = cm(z, torch.tensor([own]), xyz)
+        b = cm(z, torch.tensor([own], dtype=torch.int32, device=DEV), xyz)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)

@@ -280,3 +280,60 @@ def test_train_step_reads_no_uninitialised_memory(kind):
     loss.backward()
     bad = [n for n, p in model.named_parameters() if p.grad is not None and not bool(torch.isfinite(p.grad).all())]
     assert not bad, bad
+
+
+def test_graphed_mvs_supervised_step_matches_eager_across_the_annealing_switch():
+    """The paper configuration's step (vsdf.py:205-211 with use_mvs; loss.py:80-115 with sparse_weight / anneal_rgb): forward,
+    CostMapper, VolSDFLoss (GCE on the weights + annealed sparsity prior + photometric term on uncertain rays), backward,
+    clip, Adam — as ONE CUDA graph whose replays change the batch image and cross `iter_step == anneal_rgb` — against the
+    same steps issued eagerly with the host-side VolSDFLoss.forward (itself pinned to the reference's loss in
+    test_oracle_vs_golden.py)."""
+    from svolsdf_b200.model.loss import VolSDFLoss
+    from svolsdf_b200.model.ray_sampler import RecordedRng, RefRng, TapeRng
+    from svolsdf_b200.mvs import CostMapper
+    from svolsdf_b200.optim import FusedAdam
+    from svolsdf_b200.train import GraphedTrainStep
+    R = 256
+    inp = {k: v.to(DEV) for k, v in S.make_input('dtu', R).items()}
+    gt = {'rgb': S.gt_rgb(R).to(DEV), 'rgb_smooth': S.gt_rgb(R, seed=5).to(DEV)}
+    views = S.mvs_views(n_views=3, dz=16, h=36, w=48, img_res=(1200, 1600), seed=9)
+    ids = [25, 22, 28]
+    cm = CostMapper([v['cost'][None] for v in views], [v['z_mvs'][None] for v in views], [v['K'] for v in views],
+                    [v['c2w'] for v in views], ids, (1200, 1600), inverse_depth=True)
+    kw = dict(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=1.0, sparse_weight=1.0, anneal_rgb=2, gce=0.5)
+    models, opts = [], []
+    for _ in range(2):
+        m = build_model('dtu', perturb=True, beta=0.05, device=DEV).train().set_engine(L.ENGINE_TC_SPLIT)
+        models.append(m)
+        opts.append(FusedAdam(m.parameters(), lr=5e-4, max_grad_norm=1.0))
+    torch.manual_seed(11)
+    tapes = []
+    for _ in range(4):
+        tr = TapeRng(RefRng(DEV))
+        models[0].rng_source = tr
+        with torch.no_grad():
+            models[0](inp, fast=1)
+        tapes.append(tr.tape)
+    owns = [22, 25, 28, 22]
+    # eager, host-side loss module
+    loss_e = VolSDFLoss(**kw)
+    losses_e = []
+    for t, own in zip(tapes, owns):
+        models[0].rng_source = RecordedRng(DEV, t)
+        out = models[0](inp, fast=1)
+        out['pj'], out['pi'], _ = cm(out['depth_vals'], torch.tensor([own]), out['xyz'])
+        res = loss_e(out, gt)
+        opts[0].zero_grad(set_to_none=True)
+        res['loss'].backward()
+        opts[0].step()
+        losses_e.append(float(res['loss']))
+    assert loss_e.iter_step == 4
+    # graphed
+    step = GraphedTrainStep(models[1], opts[1], VolSDFLoss(**kw), inp, gt, grad_clip=0.0, cost_mapper=cm, own_view=owns[0])
+    losses_g = [float(step(inp, gt, t, own_view=own)) for t, own in zip(tapes, owns)]
+    assert float(step.iter_step) == 4.0
+    # (identical kernels; after 3 Adam steps the parameters differ by the order of the fp32 atomics in the weight-gradient
+    # kernel, ~2e-5 in the loss — see test_graphed_train_step_matches_eager)
+    assert max(abs(a - b) for a, b in zip(losses_e[:2], losses_g[:2])) < 1e-6, (losses_e, losses_g)
+    assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 1e-4, (losses_e, losses_g)
+    assert abs(losses_e[1] - losses_e[2]) > 1e-3       # the annealing switch changes the loss (both paths follow it)

@@ -282,3 +282,23 @@ def test_loss_module_gradients_match_oracle(gce):
     for k in keys:
         assert grads[1][k].abs().max() > 0
         assert max_abs(grads[0][k], grads[1][k]) < 1e-12, k
+
+
+def test_loss_forward_device_equals_forward_on_every_side_of_the_annealing_switch():
+    """VolSDFLoss.forward_device (device-side iteration counter, no host branch: CUDA-graph capturable) == forward"""
+    from svolsdf_b200.model.loss import VolSDFLoss
+    g = torch.Generator().manual_seed(0)
+    R, S_ = 64, 98
+    out = {'rgb_values': torch.rand(R, 3, generator=g), 'grad_theta': torch.randn(2 * R, 3, generator=g),
+           'weights': torch.softmax(torch.randn(R, S_, generator=g), 1), 'depth_values': torch.rand(R, 1, generator=g) + 1,
+           'pi': torch.rand(R, S_, generator=g) * (torch.rand(R, 1, generator=g) > 0.3), 'pj': torch.rand(R, S_, generator=g)}
+    gt = {'rgb': torch.rand(1, R, 3, generator=g), 'rgb_smooth': torch.rand(1, R, 3, generator=g)}
+    for kw in (dict(mvs_weight=1.0, sparse_weight=1.0, anneal_rgb=3, gce=0.5), dict(mvs_weight=0.5, sparse_weight=0.0, gce=1),
+               dict(mvs_weight=0.0, sparse_weight=2.0, anneal_rgb=2, gce=0)):
+        a = VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1, **kw)
+        b = VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1, **kw)
+        for it in range(5):
+            ra = a(out, gt)
+            rb = b.forward_device(out, gt, torch.tensor(float(it)))
+            for k in ra:
+                assert abs(float(ra[k]) - float(rb[k])) < 1e-6, (kw, it, k)
