@@ -231,7 +231,10 @@ __global__ void pe_grad_kernel(const float* __restrict__ x, const float* __restr
     float sphere = sph_scale * (radius - nrm);
     float w = clamp_factor(y0, sphere, true);
     out_sdf = fminf(y0, sphere);
-    for (int d = 0; d < d_in; ++d) g[d] = w * g[d] + (1.f - w) * (-sph_scale * xv[d] / nrm);
+    // the sphere branch only where it is taken (w < 1): at x = 0 its gradient is 0/0, and autograd's norm backward
+    // masks |x| = 0 to a zero gradient
+    if (w < 1.f)
+      for (int d = 0; d < d_in; ++d) g[d] = w * g[d] + (1.f - w) * (nrm > 0.f ? -sph_scale * xv[d] / nrm : 0.f);
   }
   if (sdf) sdf[m] = out_sdf;
   if (grad)
@@ -482,8 +485,9 @@ extern "C" int64_t svs_sdf_bwd_ws_floats(const svs_mlp_desc* d, int64_t P, int e
   return P * ((int64_t)lo.ld0 + (int64_t)(4 + lo.L - 1) * lo.H + lo.ldy);
 }
 
-static int check_sdf(const svs_mlp_desc* d, const Layout& lo, int engine) {
+static int check_sdf(const svs_mlp_desc* d, const Layout& lo, int engine, int64_t P = 0) {
   SVS_CHECK_ARG(d->kind == SVS_NET_SDF, "descriptor is not an SDF net");
+  SVS_CHECK_ARG(P >= 0 && P <= 2147483647LL - 128, "point count %lld exceeds the 2^31 - 1 rows one launch can address", (long long)P);
   SVS_CHECK_ARG(engine_ok(engine), "engine %d not built", engine);
   if (engine == SVS_ENGINE_FP32)
     for (int l = 1; l < lo.L; ++l) SVS_CHECK_ARG(lo.ldi[l] == lo.H, "hidden widths must be uniform (layer %d)", l);
@@ -494,7 +498,7 @@ extern "C" int svs_sdf_forward(const svs_mlp_desc* d, const float* wbuf, const f
                                float* sdf, float* ws, int engine, void* stream) {
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
-  SVS_TRY(check_sdf(d, lo, engine));
+  SVS_TRY(check_sdf(d, lo, engine, P));
   SVS_CHECK_ARG(wbuf && x && ws && (y || sdf) && P >= 0, "svs_sdf_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -557,7 +561,7 @@ extern "C" int svs_sdf_outputs_forward(const svs_mlp_desc* d, const float* wbuf,
                                        void* stream) {
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
-  SVS_TRY(check_sdf(d, lo, engine));
+  SVS_TRY(check_sdf(d, lo, engine, P));
   SVS_CHECK_ARG(wbuf && x && y && ws && P >= 0, "svs_sdf_outputs_forward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -656,7 +660,7 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
                                         const float* d_grad, float* dwbuf, float* ws, int engine, void* stream) {
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
-  SVS_TRY(check_sdf(d, lo, engine));
+  SVS_TRY(check_sdf(d, lo, engine, P));
   SVS_CHECK_ARG(wbuf && x && saved && y && dwbuf && ws && P >= 0, "svs_sdf_outputs_backward: bad arguments");
   if (P == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -757,7 +761,8 @@ extern "C" int svs_sdf_outputs_backward(const svs_mlp_desc* d, const float* wbuf
 // rendering network
 // ---------------------------------------------------------------------------------------------------
 
-static int check_render(const svs_mlp_desc* d, const Layout& lo, int engine, int* pe_v, int* F) {
+static int check_render(const svs_mlp_desc* d, const Layout& lo, int engine, int* pe_v, int* F, int64_t P = 0) {
+  SVS_CHECK_ARG(P >= 0 && P <= 2147483647LL - 128, "point count %lld exceeds the 2^31 - 1 rows one launch can address", (long long)P);
   SVS_CHECK_ARG(d->kind == SVS_NET_RENDER, "descriptor is not a rendering net");
   SVS_CHECK_ARG(engine_ok(engine), "engine %d not built", engine);
   *pe_v = 3 * (1 + 2 * d->n_freqs);
@@ -798,7 +803,7 @@ extern "C" int svs_render_forward(const svs_mlp_desc* d, const float* wbuf, cons
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
   int pe_v, F;
-  SVS_TRY(check_render(d, lo, engine, &pe_v, &F));
+  SVS_TRY(check_render(d, lo, engine, &pe_v, &F, P));
   const int idr = d->render_mode == SVS_RENDER_IDR;
   SVS_CHECK_ARG(wbuf && view_dirs && feat && rgb && saved && P >= 0, "svs_render_forward: bad arguments");
   SVS_CHECK_ARG(!idr || (points && normals), "svs_render_forward: idr mode needs points and normals");
@@ -847,7 +852,7 @@ extern "C" int svs_render_backward(const svs_mlp_desc* d, const float* wbuf, int
   Layout lo;
   SVS_TRY(make_layout(d, &lo));
   int pe_v, F;
-  SVS_TRY(check_render(d, lo, engine, &pe_v, &F));
+  SVS_TRY(check_render(d, lo, engine, &pe_v, &F, P));
   const int idr = d->render_mode == SVS_RENDER_IDR;
   SVS_CHECK_ARG(wbuf && saved && rgb && d_rgb && dwbuf && ws && P >= 0, "svs_render_backward: bad arguments");
   if (P == 0) return SVS_OK;

@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             float out_sdf = y0;
             if (clamp_on) {
               out_sdf = fminf(y0, sphere);
-              for (int d = 0; d < ch.d_in; ++d) g[d] = cw * g[d] + (1.f - cw) * (-ch.sph_scale * xv[d] / nrm);
+              if (cw < 1.f)   // sphere branch only where taken; |x| = 0 has a zero gradient (norm backward masks it)
+                for (int d = 0; d < ch.d_in; ++d) g[d] = cw * g[d] + (1.f - cw) * (nrm > 0.f ? -ch.sph_scale * xv[d] / nrm : 0.f);
             }
             if (ch.sdf) ch.sdf[p] = out_sdf;
             if (ch.grad)

@@ -2,7 +2,7 @@
 
 The Python side only owns the outer loop of Algorithm 1 (each iteration needs the SDF network) and the
 reference's CPU random draws; every per-ray computation runs in the warp-per-ray kernels of
-csrc/sampler.cu.  Training (`fast=1`) has no host synchronisation at all; evaluation reads one 4-byte
+csrc/sampler.cu.  Training (`fast=1`) has no host synchronisation; evaluation reads one 4-byte
 convergence flag per iteration (the reference synchronises ~47 times per iteration).
 """
 import abc

@@ -66,9 +66,18 @@ def test_raygen_and_sphere():
         assert max_abs(d2.cpu(), rd) < 1e-6 and max_abs(c2.cpu(), cl) == 0
         nf = rend_util.get_sphere_intersections(c, d, r=3.0)
         assert max_abs(nf.cpu(), O.get_sphere_intersections(cl.expand(500, 3), rd[0], 3.0)) < 1e-5
-    # a ray that misses the sphere must raise where the reference exit()s
-    with pytest.raises(RuntimeError):
-        rend_util.get_sphere_intersections(torch.tensor([[10., 0, 0]], device=DEV), torch.tensor([[0., 1, 0]], device=DEV), r=1.0)
+    # a ray that misses the sphere must raise where the reference exit()s: at once outside training ...
+    miss = (torch.tensor([[10., 0, 0]], device=DEV), torch.tensor([[0., 1, 0]], device=DEV))
+    with torch.no_grad():
+        with pytest.raises(RuntimeError):
+            rend_util.get_sphere_intersections(*miss, r=1.0)
+    # ... and without a host synchronisation inside a training step: the condition sticks to a device flag
+    with torch.enable_grad():
+        rend_util.get_sphere_intersections(*miss, r=1.0)
+        rend_util.get_sphere_intersections(c, d, r=3.0)
+        with pytest.raises(RuntimeError):
+            rend_util.check_bounding_sphere()
+        rend_util.check_bounding_sphere()      # reading clears it
 
 
 def test_embed_and_density(dtu):
