@@ -619,6 +619,9 @@ def run_ours(args):
             e = {'kernel': name, 'avg_launch_ms': v['ms'] / v['launches'], 'traffic': tr,
                  'tensor_frac': f_t, 'hbm_frac': f_h if gb > 0 else None,
                  'hbm_frac_measured_traffic': (tr / (v['ms'] / v['launches'] * 1e-3) / 1e9 / pk['hbm_gbs']) if tr else None}
+            if engine == L.ENGINE_TC_SPLIT and name in ('mlp_tc_sdf_fwd', 'mlp_tc_render_fwd'):
+                # split-operand chains issue 3 MMAs per algorithmic one (the roofline fraction counts them once)
+                e['mma_issued_frac_of_tensor_peak'] = 3.0 * f_t
             if name.startswith(MLP_KERNELS) and v['flops'] > 0:
                 e.update({'bound': 'tensor', 'achieved': tf, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                           'frac': f_t, 'peak_source': pk['source'] + ' bf16 sustained'})

@@ -90,6 +90,7 @@ struct TcStep {
   const uint8_t* w;    // KB blocks of n_pad x 128 bytes
   const uint8_t* w_lo; // split-operand chains (SVS_ENGINE_TC_SPLIT, mlp_tc_fwd3.cuh): the image of W - fp16(W), same geometry
   const float* bias;   // fp32[n_valid] or nullptr
+  const float* bias_t; // split softplus steps: fp32[n_pad] = bias * 100 log2(e) (16-byte aligned)
   int32_t KB, n_pad, n_valid, epi;
   float scale, hscale;
   int32_t n_split;

@@ -29,7 +29,10 @@ static void add_sdf_forward_steps(TcChain* ch, const Layout& lo, const WImages& 
   for (int l = 0; l < lo.L - 1; ++l) {
     TcStep s = make_step(reg + wi.fwd[l], wbuf + lo.boff[l], wi.fwd_kb[l], wi.fwd_npad[l], lo.out[l], EP_SOFTPLUS);
     s.next_kb = kb_of(lo.in[l + 1]);
-    if (split) s.w_lo = reg + wi.fwd_lo[l];
+    if (split) {
+      s.w_lo = reg + wi.fwd_lo[l];
+      s.bias_t = reinterpret_cast<const float*>(reg + wi.fwd_bt[l]);
+    }
     if (l + 1 == lo.skip) {
       s.scale = kInvSqrt2;
       s.flags = TC_PEFILL;

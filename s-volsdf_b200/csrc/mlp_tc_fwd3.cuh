@@ -97,6 +97,7 @@ static bool fwd3_supports(const TcChain& ch) {
     if (!st.w_lo || st.KB > max_kb || st.next_kb > max_kb || st.n_pad > 256 || st.colsum >= 0 || st.aux1 >= 0 || st.aux2 >= 0) return false;
     if (st.epi == (render ? EP_RELU : EP_SOFTPLUS)) {
       if (st.next_kb <= 0 || s + 1 >= ch.n_steps || st.next_kb != ch.st[s + 1].KB) return false;
+      if (!render && !st.bias_t) return false;
     } else if (render ? st.epi == EP_RGB : (st.epi == EP_SDF || st.epi == EP_Y)) {
       if (st.next_kb != 0 || (s + 1 < ch.n_steps && ch.st[s + 1].KB != st.KB)) return false;
     } else {
@@ -119,6 +120,9 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
   F3Bars* bars = reinterpret_cast<F3Bars*>(smem + Cfg::kOffBar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // chains that save nothing (sampler sdf, eval forward): no store lane, no hand-back of the blocks
+  bool any_save = ch.pro_save >= 0;
+  for (int s = 0; s < ch.n_steps; ++s) any_save |= ch.st[s].save >= 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     }
   } else if (warp == 3) {
     // ===== store lane: saves the hi half of every generation of A the backward needs, then frees the blocks =====
-    if (lane == 0) {
+    if (lane == 0 && any_save) {
       uint32_t a_par = 0;
       auto consume = [&](int kb) {
         for (int bi = kb * 4; bi < kb * 4 + 4; ++bi) {
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           const int b = pc >> 2, c0 = pc * 16;
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_eval_precise(xv, petab[c0 + i]) : 0.f;
-          mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
+          if (any_save) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
           st_row16_split(sAhi + b * kBlk, sAlo + b * kBlk, m, pc & 3, v);
           fence_proxy_async();
           __syncwarp();
@@ -313,7 +317,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
       } else {
         // A = [feat (F columns) | points(3) if idr, PE(view), normals(3) if idr].  Features are fp32 row-major: warp ew
         // converts rows 8 ew .. 8 ew + 7, a lane reads columns lane, lane + 32, ... (one 128-byte line per instruction).
-        for (int b = 0; b < ch.pro_kb; ++b) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
+        if (any_save)
+          for (int b = 0; b < ch.pro_kb; ++b) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
         const int64_t trow0 = (int64_t)t * kTile;
         for (int rb = 0; rb < 8; rb += 2) {
           float fv[2][8];
@@ -384,8 +389,9 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         // the zero-mean part of the truncation, which does not add up over the layers: sdf error 4.8e-6 -> 9.6e-7 in
         // the CPU model of this arithmetic.
         const float rz = 1.0f + 2.1496e-8f * (float)(4 * st.KB + 1);
+        const float rzk = rz * kSpK1;
         const uint32_t tm_acc = tm_row + (n_acc & 1) * 256;
-        mbar_wait(&bars->acc_full, n_acc & 1);
+        mbar_wait_relaxed(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
         if (!writes_a && has_next) {
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           if (col0 < st.n_pad) {
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rr[i]) * rz;
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(rr[i]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -412,28 +418,30 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           if constexpr (MODE == kF2Sdf) {
             if (st.epi == EP_SOFTPLUS) {
               if (col0 + 16 <= st.n_valid) {
-                const float4* b4 = reinterpret_cast<const float4*>(st.bias + col0);
+                // t = 100 log2(e) (acc rz + b) as ONE FFMA per element: rz 100 log2(e) is uniform, b 100 log2(e) comes
+                // from the table the weight packer wrote
+                const float4* b4 = reinterpret_cast<const float4*>(st.bias_t + col0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float4 b = __ldg(b4 + i);
-                  o[4 * i + 0] = softplus_t2((acc[4 * i + 0] + b.x) * kSpK1, csp);
-                  o[4 * i + 1] = softplus_t2((acc[4 * i + 1] + b.y) * kSpK1, csp);
-                  o[4 * i + 2] = softplus_t2((acc[4 * i + 2] + b.z) * kSpK1, csp);
-                  o[4 * i + 3] = softplus_t2((acc[4 * i + 3] + b.w) * kSpK1, csp);
+                  o[4 * i + 0] = softplus_t2(fmaf(acc[4 * i + 0], rzk, b.x), csp);
+                  o[4 * i + 1] = softplus_t2(fmaf(acc[4 * i + 1], rzk, b.y), csp);
+                  o[4 * i + 2] = softplus_t2(fmaf(acc[4 * i + 2], rzk, b.z), csp);
+                  o[4 * i + 3] = softplus_t2(fmaf(acc[4 * i + 3], rzk, b.w), csp);
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const int n = col0 + i;
                   float v = 0.f;
-                  if (n < st.n_valid) v = softplus_t2((acc[i] + __ldg(st.bias + n)) * kSpK1, csp);
+                  if (n < st.n_valid) v = softplus_t2(fmaf(acc[i], rzk, __ldg(st.bias_t + n)), csp);
                   else if ((st.flags & TC_PEFILL) && n - st.n_valid < pe_w) v = pe_eval_precise(xv, petab[n - st.n_valid]) * st.scale;
                   o[i] = v;
                 }
               }
             } else if (st.epi == EP_SDF) {
               if (col0 == 0 && live) {
-                float y0 = acc[0] + __ldg(st.bias);
+                float y0 = fmaf(acc[0], rz, __ldg(st.bias));
                 if (ch.radius > 0.f && p < ch.n_clamped) {
                   const float n2 = xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2] + xv[3] * xv[3];
                   y0 = fminf(y0, ch.sph_scale * (ch.radius - sqrtf(n2)));
@@ -442,20 +450,20 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               }
             } else {   // EP_Y
               if (st.n_valid == 1) {
-                if (col0 == 0 && live) ch.y[p * ch.ldy + st.y_col] = acc[0] + __ldg(st.bias);
+                if (col0 == 0 && live) ch.y[p * ch.ldy + st.y_col] = fmaf(acc[0], rz, __ldg(st.bias));
               } else if (has_next) {   // a later step still multiplies A: no scratch, direct stores
                 if (live) {
                   float* dst = ch.y + p * ch.ldy + st.y_col + col0;
 #pragma unroll
                   for (int i = 0; i < 16; ++i)
-                    if (col0 + i < st.n_valid) dst[i] = acc[i] + __ldg(st.bias + col0 + i);
+                    if (col0 + i < st.n_valid) dst[i] = fmaf(acc[i], rz, __ldg(st.bias + col0 + i));
                 }
               } else {
                 // coalesced fp32 row-major stores: transpose the 32 x 16 piece through this warp's scratch inside A_lo
                 // (idle: every MMA of the tile has completed, and A_lo is never saved)
                 float* scr = reinterpret_cast<float*>(sAlo) + ew * (32 * 17);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) scr[lane * 17 + i] = acc[i] + ((col0 + i < st.n_valid) ? __ldg(st.bias + col0 + i) : 0.f);
+                for (int i = 0; i < 16; ++i) scr[lane * 17 + i] = fmaf(acc[i], rz, (col0 + i < st.n_valid) ? __ldg(st.bias + col0 + i) : 0.f);
                 __syncwarp();
                 const int cc = lane & 15, n = col0 + cc;
                 const int64_t row0 = p - lane;
@@ -475,27 +483,27 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const float4 b = __ldg(b4 + i);
-                  o[4 * i + 0] = fmaxf(acc[4 * i + 0] + b.x, 0.f);
-                  o[4 * i + 1] = fmaxf(acc[4 * i + 1] + b.y, 0.f);
-                  o[4 * i + 2] = fmaxf(acc[4 * i + 2] + b.z, 0.f);
-                  o[4 * i + 3] = fmaxf(acc[4 * i + 3] + b.w, 0.f);
+                  o[4 * i + 0] = fmaxf(fmaf(acc[4 * i + 0], rz, b.x), 0.f);
+                  o[4 * i + 1] = fmaxf(fmaf(acc[4 * i + 1], rz, b.y), 0.f);
+                  o[4 * i + 2] = fmaxf(fmaf(acc[4 * i + 2], rz, b.z), 0.f);
+                  o[4 * i + 3] = fmaxf(fmaf(acc[4 * i + 3], rz, b.w), 0.f);
                 }
               } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = (col0 + i < st.n_valid) ? fmaxf(acc[i] + __ldg(st.bias + col0 + i), 0.f) : 0.f;
+                for (int i = 0; i < 16; ++i) o[i] = (col0 + i < st.n_valid) ? fmaxf(fmaf(acc[i], rz, __ldg(st.bias + col0 + i)), 0.f) : 0.f;
               }
             } else {   // EP_RGB
               if (live) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const int n = col0 + i;
-                  if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + expf(-(acc[i] + __ldg(st.bias + n))));
+                  if (n < st.n_valid) ch.rgb[p * st.n_valid + n] = 1.0f / (1.0f + expf(-fmaf(acc[i], rz, __ldg(st.bias + n))));
                 }
               }
             }
           }
           if (writes_a && c < st.next_kb) {
-            mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
+            if (any_save) mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
             st_row16_split(sAhi + c * kBlk, sAlo + c * kBlk, m, pc & 3, o);
             fence_proxy_async();
             tc_fence_before();

@@ -37,6 +37,7 @@ struct WImages {
   int64_t bwd[SVS_MAX_LAYERS];   // B[n = in][k = out]   (rendering layer 0: the feature columns)
   int64_t fwd_sdf;               // SDF last layer, row 0 padded to 16 rows
   int64_t fwd_lo[SVS_MAX_LAYERS], fwd_sdf_lo;   // split engine: images of W - fp16(W) (behind all regular images)
+  int64_t fwd_bt[SVS_MAX_LAYERS];               // split engine, SDF softplus layers: fp32 table bias * 100 log2(e), n_pad entries
   int64_t bwd_small;             // rendering layer 0: the non-feature input columns
   int fwd_npad[SVS_MAX_LAYERS], fwd_kb[SVS_MAX_LAYERS];
   int bwd_npad[SVS_MAX_LAYERS], bwd_kb[SVS_MAX_LAYERS];
@@ -138,6 +139,11 @@ static int make_wimages(const svs_mlp_desc* d, const Layout& lo, WImages* wi, Pa
         wi->fwd_lo[l] = add_lo(wi->fwd_npad[l], wi->fwd_kb[l], l, 0, lo.out[l], (l == 0) ? wi->F + wi->n_small : lo.in[l],
                                (l == 0) ? wi->F : 0, (l == 0) ? wi->n_small : 0);
     }
+    if (d->kind == SVS_NET_SDF)
+      for (int l = 0; l < L - 1; ++l) {
+        wi->fwd_bt[l] = off;
+        if (split) off += round_up((int64_t)wi->fwd_npad[l] * 4, 1024);
+      }
   }
   wi->bytes = off;
   if (n_list) *n_list = n;
@@ -172,6 +178,17 @@ __global__ void pack_images_kernel(const PackArgsTc a, const float* __restrict__
   }
 }
 
+// split engine: softplus biases pre-multiplied by 100 log2(e) (the epilogue computes t = acc * c + bias_t in one FFMA)
+struct BiasTArgs {
+  long long src[SVS_MAX_LAYERS], dst[SVS_MAX_LAYERS];
+  int n[SVS_MAX_LAYERS], n_pad[SVS_MAX_LAYERS], count;
+};
+__global__ void pack_bias_t_kernel(const BiasTArgs a, const float* __restrict__ wbuf, uint8_t* __restrict__ region) {
+  const int l = blockIdx.x;
+  float* dst = reinterpret_cast<float*>(region + a.dst[l]);
+  for (int i = threadIdx.x; i < a.n_pad[l]; i += blockDim.x) dst[i] = i < a.n[l] ? wbuf[a.src[l] + i] * kSpK1 : 0.f;
+}
+
 static int64_t wbuf_floats_tc(const svs_mlp_desc* d, const Layout& lo, bool split) {
   WImages wi;
   if (make_wimages(d, lo, &wi, nullptr, nullptr, split) != SVS_OK) return -1;
@@ -195,6 +212,19 @@ static int pack_images(const svs_mlp_desc* d, const Layout& lo, float* wbuf, cud
   }
   pack_images_kernel<<<dim3(32, n), 256, 0, st>>>(a, wbuf, wimg_region(lo, wbuf));
   SVS_LAUNCH_OK();
+  if (split && d->kind == SVS_NET_SDF && lo.L > 1) {
+    BiasTArgs b;
+    memset(&b, 0, sizeof(b));
+    b.count = lo.L - 1;
+    for (int l = 0; l < lo.L - 1; ++l) {
+      b.src[l] = lo.boff[l];
+      b.dst[l] = wi.fwd_bt[l];
+      b.n[l] = lo.out[l];
+      b.n_pad[l] = wi.fwd_npad[l];
+    }
+    pack_bias_t_kernel<<<b.count, 256, 0, st>>>(b, wbuf, wimg_region(lo, wbuf));
+    SVS_LAUNCH_OK();
+  }
   return SVS_OK;
 }
 
