@@ -13,6 +13,7 @@
 namespace svs {
 
 constexpr int kCompWarps = 4;
+constexpr int kCompStages = 3;   // rows of the warp's next TWO rays are in flight while the current one is composited
 
 // per-warp input rows of one ray (z has one pad element for the i + 1 access); `g` is the normals row (forward, eval)
 // or the dL/dweights row (backward)
@@ -21,13 +22,15 @@ struct CompRows {
   float z[32 * C + 4];
   float s[32 * C];
   float c[32 * C * 3];
-  float g[(G > 0 ? 32 * C * G : 1) + 3];   // G floats per sample: 3 = normals (eval forward), 1 = dL/dweights (backward), 0 = unused
+  float g[(G > 0 ? 32 * C * G : 0) + 4];   // G floats per sample: 3 = normals (eval forward), 1 = dL/dweights (backward), 0 = unused;
+                                           // every array is a multiple of 16 bytes: lanes read their chunk with 128-bit loads
 };
-// two stages per warp: the rows of the warp's NEXT ray land (cp.async, no registers) while the current ray is being
-// composited, so a warp's HBM latency overlaps its own arithmetic; + one output row
+// kCompStages stages per warp: the rows of the warp's next rays land (cp.async, no registers) while the current ray is
+// being composited, so a warp's HBM latency overlaps its own arithmetic (one ray ahead left the kernel latency-bound:
+// a ray took ~5.9 k cycles per warp of which ~0.5 k were arithmetic); + one output row
 template <int C, int G>
 struct CompSmem {
-  CompRows<C, G> in[kCompWarps][2];
+  CompRows<C, G> in[kCompWarps][kCompStages];
   float w[kCompWarps][32 * C];
   float o[kCompWarps][32 * C];
 };
@@ -66,6 +69,34 @@ __device__ __forceinline__ void issue_rows(CompRows<C, G>& st, const float* __re
     }
   }
   cp_async_commit();
+}
+
+// a lane's N consecutive floats of a staged row starting at row[first] (first % 4 == 0 when N % 4 == 0): 128-bit loads.
+// A scalar read of row[lane * C + j] walks the banks with stride C — a 4-way conflict for the C = 4 of DTU rows (ncu: 15.5 M
+// conflicts per launch, LSU pipe 34 % busy).
+template <int N>
+__device__ __forceinline__ void ld_chunk(const float* row, int first, float (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(row + first + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = row[first + j];
+  }
+}
+template <int N>
+__device__ __forceinline__ void st_chunk(float* row, int first, const float (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      *reinterpret_cast<float4*>(row + first + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) row[first + j] = v[j];
+  }
 }
 
 __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min) {
@@ -163,46 +194,51 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
   const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
   // rows shorter than the padded width read as zeros: the copies never touch the pad
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kCompStages; ++k) {
     CompRows<C, G>& st = sm.in[warp][k];
     for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
     for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
   }
   __syncwarp();
   const float* nrm_rows = normal_map ? normals : nullptr;
-  if (ray0 < R)
-    issue_rows<C, G>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
-                  nrm_rows ? nrm_rows + ray0 * S * 3 : nullptr, 3 * S, S, lane);
-  float n_ds = (depth_scale && ray0 < R) ? __ldg(depth_scale + ray0) : 1.f;
-  float n_zmax = (tail && ray0 < R) ? __ldg(z_max + ray0) : 0.f;
-  int k = 0;
-  for (int64_t ray = ray0; ray < R; ray += stride, k ^= 1) {
-    const float ds = n_ds, zmax = n_zmax;
-    const int64_t nxt = ray + stride;
-    if (nxt < R) {   // the next ray's rows and per-ray scalars are in flight while this ray is composited
-      issue_rows<C, G>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
-                    nrm_rows ? nrm_rows + nxt * S * 3 : nullptr, 3 * S, S, lane);
-      if (depth_scale) n_ds = __ldg(depth_scale + nxt);
-      if (tail) n_zmax = __ldg(z_max + nxt);
-      cp_async_wait<1>();
+  // one commit group per ray (empty past the end), so `wait_group kCompStages - 1` always means "the current ray landed"
+  auto issue = [&](int64_t r, int stage, float* ds_out, float* zmax_out) {
+    if (r < R) {
+      issue_rows<C, G>(sm.in[warp][stage], z + r * S, sdf + r * S, rgb ? rgb + r * S * 3 : nullptr,
+                       nrm_rows ? nrm_rows + r * S * 3 : nullptr, 3 * S, S, lane);
+      *ds_out = depth_scale ? __ldg(depth_scale + r) : 1.f;
+      *zmax_out = tail ? __ldg(z_max + r) : 0.f;
     } else {
-      cp_async_wait<0>();
+      cp_async_commit();
     }
+  };
+  float ds_q[kCompStages - 1] = {1.f, 1.f}, zm_q[kCompStages - 1] = {0.f, 0.f};
+  issue(ray0, 0, &ds_q[0], &zm_q[0]);
+  issue(ray0 + stride, 1, &ds_q[1], &zm_q[1]);
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k = (k + 1 == kCompStages) ? 0 : k + 1) {
+    const float ds = ds_q[0], zmax = zm_q[0];
+    ds_q[0] = ds_q[1];
+    zm_q[0] = zm_q[1];
+    issue(ray + 2 * stride, (k + 2) % kCompStages, &ds_q[1], &zm_q[1]);
+    cp_async_wait<kCompStages - 1>();
     __syncwarp();
     const CompRows<C, G>& in = sm.in[warp][k];
     using ScanT = typename std::conditional<FAST, float, double>::type;
-    float E[C], zz[C];
+    float E[C], zz[C], sv[C];
     ScanT excl[C];
+    ld_chunk<C>(in.z, lane * C, zz);
+    ld_chunk<C>(in.s, lane * C, sv);
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, zz[0], 1);   // z[C (lane + 1)]; unused for the last lane (i >= S - 1)
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float zi = in.z[i];
-      zz[j] = zi;
+      float zi = zz[j];
       float em;
-      float sigma = density_fwd<FAST>(in.s[i], beta, abs_d, &em);
+      float sigma = density_fwd<FAST>(sv[j], beta, abs_d, &em);
       float d;
       if (i < S - 1) {
-        float zn = in.z[i + 1];
+        float zn = (j + 1 < C) ? zz[(j + 1) % C] : z_next_lane;
         d = rev ? (zi - zn) : (zn - zi);
       } else if (i == S - 1) {
         d = tail ? (zmax - zi) : 1e10f;
@@ -213,23 +249,26 @@ composite_fwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     }
     ScanT total = warp_excl_scan<C, ScanT>(E, excl, lane);
     float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_w = 0.f, acc_wz = 0.f;
+    float cv[3 * C], wv[C];
+    if (rgb) ld_chunk<3 * C>(in.c, lane * 3 * C, cv);
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       float T = exp_t<FAST>(-(float)excl[j]);
       float a = 1.0f - exp_t<FAST>(-E[j]);
       float w = (i < S) ? a * T : 0.f;
+      wv[j] = w;
       if (i < S) {
-        sm.w[warp][i] = w;
         acc_w += w;
         acc_wz += w * zz[j];
         if (rgb) {
-          acc_r += w * in.c[3 * i];
-          acc_g += w * in.c[3 * i + 1];
-          acc_b += w * in.c[3 * i + 2];
+          acc_r += w * cv[3 * j];
+          acc_g += w * cv[3 * j + 1];
+          acc_b += w * cv[3 * j + 2];
         }
       }
     }
+    st_chunk<C>(sm.w[warp], lane * C, wv);
     __syncwarp();
     for (int i = lane; i < S; i += 32) weights[ray * S + i] = sm.w[warp][i];   // coalesced (the lane-contiguous layout is not)
     acc_w = warp_sum(acc_w);
@@ -289,13 +328,13 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
   const float beta = abs_d ? 1.f : beta_of(beta_param, beta_min);
   float dbeta_acc = 0.f;
   const int64_t ray0 = blockIdx.x * (int64_t)kCompWarps + warp, stride = (int64_t)gridDim.x * kCompWarps;
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kCompStages; ++k) {
     CompRows<C, G>& st = sm.in[warp][k];
     for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
     for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
   }
   __syncwarp();
-  // per-ray scalars of the NEXT ray are fetched together with its rows
+  // per-ray scalars of the next rays are fetched together with their rows
   struct RayScal { float gr, gg, gb, gdep, gbt, ds, zmax; };
   auto load_scal = [&](int64_t ray) {
     RayScal q;
@@ -308,24 +347,24 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     q.zmax = tail ? __ldg(z_max + ray) : 0.f;
     return q;
   };
-  RayScal nq = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
-  if (ray0 < R) {
-    issue_rows<C, G>(sm.in[warp][0], z + ray0 * S, sdf + ray0 * S, rgb ? rgb + ray0 * S * 3 : nullptr,
-                  d_weights ? d_weights + ray0 * S : nullptr, S, S, lane);
-    nq = load_scal(ray0);
-  }
-  int k = 0;
-  for (int64_t ray = ray0; ray < R; ray += stride, k ^= 1) {
-    const RayScal cq = nq;
-    const int64_t nxt = ray + stride;
-    if (nxt < R) {
-      issue_rows<C, G>(sm.in[warp][k ^ 1], z + nxt * S, sdf + nxt * S, rgb ? rgb + nxt * S * 3 : nullptr,
-                    d_weights ? d_weights + nxt * S : nullptr, S, S, lane);
-      nq = load_scal(nxt);
-      cp_async_wait<1>();
+  auto issue = [&](int64_t r, int stage, RayScal* q) {
+    if (r < R) {
+      issue_rows<C, G>(sm.in[warp][stage], z + r * S, sdf + r * S, rgb ? rgb + r * S * 3 : nullptr,
+                       d_weights ? d_weights + r * S : nullptr, S, S, lane);
+      *q = load_scal(r);
     } else {
-      cp_async_wait<0>();
+      cp_async_commit();
     }
+  };
+  RayScal q0 = {0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f}, q1 = q0;
+  issue(ray0, 0, &q0);
+  issue(ray0 + stride, 1, &q1);
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k = (k + 1 == kCompStages) ? 0 : k + 1) {
+    const RayScal cq = q0;
+    q0 = q1;
+    issue(ray + 2 * stride, (k + 2) % kCompStages, &q1);
+    cp_async_wait<kCompStages - 1>();
     __syncwarp();
     const CompRows<C, G>& in = sm.in[warp][k];
     const float gr = cq.gr, gg = cq.gg, gb = cq.gb, gdep = cq.gdep, gbt = cq.gbt, ds = cq.ds;
@@ -333,16 +372,17 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     using ScanT = typename std::conditional<FAST, float, double>::type;
     float E[C], zz[C], dl[C], sig[C], em[C], ss[C];
     ScanT excl[C];
+    ld_chunk<C>(in.z, lane * C, zz);
+    ld_chunk<C>(in.s, lane * C, ss);
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, zz[0], 1);
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
-      float zi = in.z[i];
-      zz[j] = zi;
-      ss[j] = in.s[i];
+      float zi = zz[j];
       sig[j] = density_fwd<FAST>(ss[j], beta, abs_d, &em[j]);
       float d;
       if (i < S - 1) {
-        float zn = in.z[i + 1];
+        float zn = (j + 1 < C) ? zz[(j + 1) % C] : z_next_lane;
         d = rev ? (zi - zn) : (zn - zi);
       } else if (i == S - 1) {
         d = tail ? (cq.zmax - zi) : 1e10f;
@@ -371,13 +411,16 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     const float iWt2 = __frcp_rn(Wt * Wt);
     // w_hat_i = c_i . dL/drgb + dL/dw_i + dL/ddepth * ds * (z_i*Wt - sum(wz)) / Wt^2
     float what[C], ww[C];
+    float cv[3 * C], gv[C];
+    if (rgb) ld_chunk<3 * C>(in.c, lane * 3 * C, cv);
+    if (d_weights) ld_chunk<C>(in.g, lane * C, gv);
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
       float v = 0.f;
       if (i < S) {
-        if (rgb) v = in.c[3 * i] * gr + in.c[3 * i + 1] * gg + in.c[3 * i + 2] * gb;
-        if (d_weights) v += in.g[i];
+        if (rgb) v = cv[3 * j] * gr + cv[3 * j + 1] * gg + cv[3 * j + 2] * gb;
+        if (d_weights) v += gv[j];
         v += FAST ? gdep * ds * (zz[j] * Wt - acc_wz) * iWt2 : gdep * ds * (zz[j] * Wt - acc_wz) / (Wt * Wt);
       }
       what[j] = v;
@@ -390,9 +433,11 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
     warp_suffix_scan<C, ScanT>(ww, suf, lane);
     const float bgt = tail ? exp_t<FAST>(-(float)total) : 0.f;
     float dbeta = 0.f;
+    float ov[C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       int i = lane * C + j;
+      ov[j] = 0.f;
       if (i < S) {
         float suffix = suf[j];
         float dE = what[j] * Te[j] - suffix - gbt * bgt;
@@ -412,10 +457,11 @@ composite_bwd_kernel(const float* __restrict__ z, const float* __restrict__ sdf,
             dbeta += dsig * (-sig[j] / beta + ss[j] * e / (2.0f * beta * beta * beta));
           }
         }
-        sm.o[warp][i] = dsdf;   // rows leave through shared memory: coalesced stores
-        sm.w[warp][i] = w[j];
+        ov[j] = dsdf;
       }
     }
+    st_chunk<C>(sm.o[warp], lane * C, ov);   // rows leave through shared memory: coalesced stores
+    st_chunk<C>(sm.w[warp], lane * C, w);
     dbeta_acc += dbeta;
     __syncwarp();
     for (int i = lane; i < S; i += 32) d_sdf[ray * S + i] = sm.o[warp][i];
