@@ -524,6 +524,435 @@ __global__ void density_bwd_kernel(const float* __restrict__ sdf, int64_t n, int
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Lean FAST forward (the common case: Laplace density, forward sample order, no z_max tail, rgb present, S even).
+// ncu on the general FAST kernel (profiles/r2_hbm_kernels_full.txt): 645 warp instructions per ray, issue slots ~70 % busy
+// at 47 % of the HBM roofline — instruction-bound, a third of it predicates / branches for the variants and 4-byte copies.
+// Here: 8-byte async copies (rows of an even S are 8-byte aligned), no per-sample branches (padding samples carry
+// dist = 0, hence E = 0, alpha = 0, w = 0), explicit FMAs (this file is compiled with -fmad=false for the canonical mode),
+// one 8-value transposing warp reduction (12 shuffles) instead of five to eight butterflies (40+), 64-bit weight stores.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kLeanWarps = 8;
+constexpr int kLeanStages = 3;
+constexpr float kL2E = 1.4426950408889634f;
+
+template <int C, bool NORMALS>
+struct LeanRows {
+  float z[32 * C + 4];
+  float s[32 * C];
+  float c[96 * C];
+  float g[NORMALS ? 96 * C : 4];
+};
+template <int C, bool NORMALS>
+struct LeanSmem {
+  LeanRows<C, NORMALS> in[kLeanWarps][kLeanStages];
+  float w[kLeanWarps][32 * C];
+};
+
+__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// sums 8 values over the warp with 3 halving exchanges + 2 butterflies; lane l ends with the total of value
+// id(l) = 4 * bit4(l) + 2 * bit3(l) + bit2(l)
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int w = 4, m = 16; w >= 1; w >>= 1, m >>= 1) {
+    const bool upper = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = upper ? v[i] : v[i + w];
+      const float keep = upper ? v[i + w] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  float r = v[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+template <int C, bool NORMALS>
+__global__ void __launch_bounds__(kLeanWarps * 32)
+composite_fwd_lean_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                          const float* __restrict__ normals, const float* __restrict__ beta_param, float beta_min,
+                          const float* __restrict__ depth_scale, int64_t R, int S, float* __restrict__ weights,
+                          float* __restrict__ rgb_values, float* __restrict__ depth_values, float* __restrict__ normal_map) {
+  extern __shared__ __align__(16) uint8_t comp_smem_raw[];
+  LeanSmem<C, NORMALS>& sm = *reinterpret_cast<LeanSmem<C, NORMALS>*>(comp_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float beta = beta_of(beta_param, beta_min);
+  const float ib = __frcp_rn(beta), kib = -kL2E * ib;
+  const int64_t ray0 = blockIdx.x * (int64_t)kLeanWarps + warp, stride = (int64_t)gridDim.x * kLeanWarps;
+  for (int k = 0; k < kLeanStages; ++k) {   // the pad behind S reads as zeros: the copies never touch it
+    LeanRows<C, NORMALS>& st = sm.in[warp][k];
+    for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
+    for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
+    for (int i = lane; i < 96 * C; i += 32) st.c[i] = 0.f;
+    if (NORMALS)
+      for (int i = lane; i < 96 * C; i += 32) st.g[i] = 1.f;
+  }
+  __syncwarp();
+  const int h1 = S >> 1, h3 = (3 * S) >> 1;   // 8-byte elements per row
+  auto issue = [&](int64_t r, int stage, float* ds_out) {
+    if (r < R) {
+      LeanRows<C, NORMALS>& st = sm.in[warp][stage];
+      const float* zr = z + r * S;
+      const float* sr = sdf + r * S;
+      const float* cr = rgb + r * S * 3;
+#pragma unroll
+      for (int j = 0; j < (C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h1) {
+          cp_async8(st.z + 2 * i, zr + 2 * i);
+          cp_async8(st.s + 2 * i, sr + 2 * i);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < (3 * C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h3) cp_async8(st.c + 2 * i, cr + 2 * i);
+      }
+      if (NORMALS) {
+        const float* gr = normals + r * S * 3;
+#pragma unroll
+        for (int j = 0; j < (3 * C + 1) / 2; ++j) {
+          const int i = lane + 32 * j;
+          if (i < h3) cp_async8(st.g + 2 * i, gr + 2 * i);
+        }
+      }
+      *ds_out = __ldg(depth_scale + r);
+    }
+    cp_async_commit();
+  };
+  float ds_q[2] = {1.f, 1.f};
+  issue(ray0, 0, &ds_q[0]);
+  issue(ray0 + stride, 1, &ds_q[1]);
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k = (k + 1 == kLeanStages) ? 0 : k + 1) {
+    const float ds = ds_q[0];
+    ds_q[0] = ds_q[1];
+    issue(ray + 2 * stride, (k + 2) % kLeanStages, &ds_q[1]);
+    cp_async_wait<kLeanStages - 1>();
+    __syncwarp();
+    const LeanRows<C, NORMALS>& in = sm.in[warp][k];
+    float zz[C], sv[C], cv[3 * C], E[C], ex[C];
+    ld_chunk<C>(in.z, lane * C, zz);
+    ld_chunk<C>(in.s, lane * C, sv);
+    ld_chunk<3 * C>(in.c, lane * 3 * C, cv);
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, zz[0], 1);
+    float run = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const int i = lane * C + j;
+      const float zn = (j + 1 < C) ? zz[(j + 1) % C] : z_next_lane;
+      float d = zn - zz[j];
+      d = (i < S - 1) ? d : ((i == S - 1) ? 1e10f : 0.f);
+      const float e = ex2_fast(fabsf(sv[j]) * kib);                         // exp(-|s| / beta)
+      const float sigma = ib * fmaf(copysignf(0.5f, sv[j]), e - 1.0f, 0.5f);   // density.py:21-26
+      E[j] = d * sigma;
+      ex[j] = run;
+      run += E[j];
+    }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    float base = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) base = 0.f;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // w, w z, r, g, b, nx, ny, nz
+    float wv[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float T = ex2_fast(-kL2E * (base + ex[j]));
+      const float w = (1.0f - ex2_fast(-kL2E * E[j])) * T;    // padding: E = 0 -> w = 0
+      wv[j] = w;
+      acc[0] += w;
+      acc[1] = fmaf(w, zz[j], acc[1]);
+      acc[2] = fmaf(w, cv[3 * j], acc[2]);
+      acc[3] = fmaf(w, cv[3 * j + 1], acc[3]);
+      acc[4] = fmaf(w, cv[3 * j + 2], acc[4]);
+    }
+    if (NORMALS) {   // eval: sum w g / |g| (network.py:270-274)
+      float gv[3 * C];
+      ld_chunk<3 * C>(in.g, lane * 3 * C, gv);
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float gx = gv[3 * j], gy = gv[3 * j + 1], gz = gv[3 * j + 2];
+        const float wn = wv[j] * rsqrtf(fmaf(gx, gx, fmaf(gy, gy, gz * gz)));
+        acc[5] = fmaf(wn, gx, acc[5]);
+        acc[6] = fmaf(wn, gy, acc[6]);
+        acc[7] = fmaf(wn, gz, acc[7]);
+      }
+    }
+    st_chunk<C>(sm.w[warp], lane * C, wv);
+    const float tot = warp_reduce8(acc, lane);      // lane l: total of value 4 bit4 + 2 bit3 + bit2
+    __syncwarp();
+    {
+      float2* wout = reinterpret_cast<float2*>(weights + ray * S);
+      const float2* wsm = reinterpret_cast<const float2*>(sm.w[warp]);
+#pragma unroll
+      for (int j = 0; j < (C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h1) wout[i] = wsm[i];
+      }
+    }
+    const float w_tot = __shfl_sync(0xffffffffu, tot, 0), wz_tot = __shfl_sync(0xffffffffu, tot, 4);
+    {
+      // lanes 0, 8, 12, 16 (, 20, 24, 28) hold depth / r / g / b (/ normal): ONE predicated store, no divergent branches
+      // (per-lane `if (lane == k)` stores cost 22 % of the kernel's stall samples in branch resolution)
+      const int id = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      const float outv = (id == 0) ? ds * (wz_tot / (w_tot + 1e-8f)) : tot;
+      float* dst = depth_values + ray;
+      if (id >= 2 && id <= 4) dst = rgb_values + ray * 3 + (id - 2);
+      if (NORMALS && id >= 5) dst = normal_map + ray * 3 + (id - 5);
+      const bool on = (lane & 3) == 0 && id != 1 && (NORMALS || id <= 4);
+      if (on) *dst = outv;
+    }
+    __syncwarp();
+  }
+}
+
+template <int C, bool NORMALS>
+static int launch_fwd_lean(const float* z, const float* sdf, const float* rgb, const float* normals, const float* beta_param,
+                           float beta_min, const float* depth_scale, int64_t R, int S, float* weights, float* rgb_values,
+                           float* depth_values, float* normal_map, cudaStream_t st) {
+  static int cap_ctas = 0;
+  const size_t smem = sizeof(LeanSmem<C, NORMALS>);
+  if (cap_ctas == 0) {
+    int per_sm = 0, sms = 0, dev = 0;
+    SVS_CUDA_OK(cudaFuncSetAttribute(composite_fwd_lean_kernel<C, NORMALS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, composite_fwd_lean_kernel<C, NORMALS>, kLeanWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = kNumSMs;
+    cap_ctas = sms * per_sm;
+  }
+  const int64_t blocks = cdiv(R, kLeanWarps);
+  composite_fwd_lean_kernel<C, NORMALS><<<(int)(blocks < cap_ctas ? blocks : cap_ctas), kLeanWarps * 32, smem, st>>>(
+      z, sdf, rgb, normals, beta_param, beta_min, depth_scale, R, S, weights, rgb_values, depth_values, normal_map);
+  return SVS_OK;
+}
+
+
+// Lean FAST backward (same restrictions as the lean forward): closed form of SURVEY.md App. G with fp32 scans, the
+// cancellation-free suffix scan, 8-byte async copies in, 64-bit coalesced stores out (d_rgb is assembled per lane as 3 C
+// consecutive floats in shared memory, conflict-free 128-bit stores).
+template <int C, bool HAS_DW>
+struct LeanBwdRows {
+  float z[32 * C + 4];
+  float s[32 * C];
+  float c[96 * C];
+  float g[HAS_DW ? 32 * C : 4];
+};
+template <int C, bool HAS_DW>
+struct LeanBwdSmem {
+  LeanBwdRows<C, HAS_DW> in[kLeanWarps][kLeanStages];
+  float o[kLeanWarps][32 * C];
+  float o3[kLeanWarps][96 * C];
+};
+
+template <int C, bool HAS_DW>
+__global__ void __launch_bounds__(kLeanWarps * 32)
+composite_bwd_lean_kernel(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                          const float* __restrict__ beta_param, float beta_min, const float* __restrict__ depth_scale,
+                          int64_t R, int S, const float* __restrict__ d_rgb_values, const float* __restrict__ d_depth_values,
+                          const float* __restrict__ d_weights, float* __restrict__ d_sdf, float* __restrict__ d_rgb,
+                          float* __restrict__ d_beta_param) {
+  extern __shared__ __align__(16) uint8_t comp_smem_raw[];
+  LeanBwdSmem<C, HAS_DW>& sm = *reinterpret_cast<LeanBwdSmem<C, HAS_DW>*>(comp_smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float beta = beta_of(beta_param, beta_min);
+  const float ib = __frcp_rn(beta), kib = -kL2E * ib, i2b2 = __frcp_rn(2.0f * beta * beta), i2b3 = i2b2 * ib;
+  const int64_t ray0 = blockIdx.x * (int64_t)kLeanWarps + warp, stride = (int64_t)gridDim.x * kLeanWarps;
+  for (int k = 0; k < kLeanStages; ++k) {
+    LeanBwdRows<C, HAS_DW>& st = sm.in[warp][k];
+    for (int i = lane; i < 32 * C + 4; i += 32) st.z[i] = 0.f;
+    for (int i = lane; i < 32 * C; i += 32) st.s[i] = 0.f;
+    for (int i = lane; i < 96 * C; i += 32) st.c[i] = 0.f;
+    if (HAS_DW)
+      for (int i = lane; i < 32 * C; i += 32) st.g[i] = 0.f;
+  }
+  __syncwarp();
+  const int h1 = S >> 1, h3 = (3 * S) >> 1;
+  struct Scal { float gr, gg, gb, gdep, ds; };
+  auto issue = [&](int64_t r, int stage, Scal* q) {
+    if (r < R) {
+      LeanBwdRows<C, HAS_DW>& st = sm.in[warp][stage];
+      const float* zr = z + r * S;
+      const float* sr = sdf + r * S;
+      const float* cr = rgb + r * S * 3;
+#pragma unroll
+      for (int j = 0; j < (C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h1) {
+          cp_async8(st.z + 2 * i, zr + 2 * i);
+          cp_async8(st.s + 2 * i, sr + 2 * i);
+          if (HAS_DW) cp_async8(st.g + 2 * i, d_weights + r * S + 2 * i);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < (3 * C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h3) cp_async8(st.c + 2 * i, cr + 2 * i);
+      }
+      q->gr = __ldg(d_rgb_values + r * 3);
+      q->gg = __ldg(d_rgb_values + r * 3 + 1);
+      q->gb = __ldg(d_rgb_values + r * 3 + 2);
+      q->gdep = __ldg(d_depth_values + r);
+      q->ds = __ldg(depth_scale + r);
+    }
+    cp_async_commit();
+  };
+  Scal q0 = {0.f, 0.f, 0.f, 0.f, 1.f}, q1 = q0;
+  issue(ray0, 0, &q0);
+  issue(ray0 + stride, 1, &q1);
+  float dbeta_acc = 0.f;
+  int k = 0;
+  for (int64_t ray = ray0; ray < R; ray += stride, k = (k + 1 == kLeanStages) ? 0 : k + 1) {
+    const Scal cq = q0;
+    q0 = q1;
+    issue(ray + 2 * stride, (k + 2) % kLeanStages, &q1);
+    cp_async_wait<kLeanStages - 1>();
+    __syncwarp();
+    const LeanBwdRows<C, HAS_DW>& in = sm.in[warp][k];
+    float zz[C], ss[C], cv[3 * C], E[C], ex[C], dl[C], sig[C], ee0[C];
+    ld_chunk<C>(in.z, lane * C, zz);
+    ld_chunk<C>(in.s, lane * C, ss);
+    ld_chunk<3 * C>(in.c, lane * 3 * C, cv);
+    const float z_next_lane = __shfl_down_sync(0xffffffffu, zz[0], 1);
+    float run = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const int i = lane * C + j;
+      const float zn = (j + 1 < C) ? zz[(j + 1) % C] : z_next_lane;
+      float d = zn - zz[j];
+      d = (i < S - 1) ? d : ((i == S - 1) ? 1e10f : 0.f);
+      dl[j] = d;
+      ee0[j] = ex2_fast(fabsf(ss[j]) * kib);                                    // e = exp(-|s| / beta) = expm1 + 1
+      sig[j] = ib * fmaf(copysignf(0.5f, ss[j]), ee0[j] - 1.0f, 0.5f);
+      E[j] = d * sig[j];
+      ex[j] = run;
+      run += E[j];
+    }
+    float incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    float base = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) base = 0.f;
+    float w[C], Te[C];
+    float acc_w = 0.f, acc_wz = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float T = ex2_fast(-kL2E * (base + ex[j]));
+      const float ee = ex2_fast(-kL2E * E[j]);
+      w[j] = (1.0f - ee) * T;
+      Te[j] = T * ee;
+      acc_w += w[j];
+      acc_wz = fmaf(w[j], zz[j], acc_wz);
+    }
+    acc_w = warp_sum(acc_w);
+    acc_wz = warp_sum(acc_wz);
+    const float Wt = acc_w + 1e-8f;
+    const float kd = cq.gdep * cq.ds * __frcp_rn(Wt * Wt);
+    // w_hat_i = c_i . dL/drgb + dL/dw_i + dL/ddepth * ds * (z_i Wt - sum(w z)) / Wt^2 ; suffix sums of w_hat_k w_k
+    float what[C], ww[C], gv[C];
+    if constexpr (HAS_DW) ld_chunk<C>(in.g, lane * C, gv);
+    float srun = 0.f, sx[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      float v = fmaf(cv[3 * j], cq.gr, fmaf(cv[3 * j + 1], cq.gg, cv[3 * j + 2] * cq.gb));
+      if constexpr (HAS_DW) v += gv[j];
+      v = fmaf(kd, fmaf(zz[j], Wt, -acc_wz), v);
+      what[j] = v;
+      ww[j] = v * w[j];        // padding: w = 0
+    }
+#pragma unroll
+    for (int j = C - 1; j >= 0; --j) {
+      sx[j] = srun;
+      srun += ww[j];
+    }
+    float sincl = srun;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float t = __shfl_down_sync(0xffffffffu, sincl, o);
+      if (lane + o < 32) sincl += t;
+    }
+    float sbase = __shfl_down_sync(0xffffffffu, sincl, 1);
+    if (lane == 31) sbase = 0.f;
+    float ov[C], o3v[3 * C];
+    float dbeta = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float dE = fmaf(what[j], Te[j], -(sbase + sx[j]));
+      const float dsig = dl[j] * dE;                          // padding: dist = 0
+      const float nz = (ss[j] != 0.f) ? 1.f : 0.f;
+      ov[j] = -dsig * nz * ee0[j] * i2b2;
+      dbeta = fmaf(dsig, fmaf(ss[j] * ee0[j], i2b3, -sig[j] * ib), dbeta);
+      o3v[3 * j] = w[j] * cq.gr;
+      o3v[3 * j + 1] = w[j] * cq.gg;
+      o3v[3 * j + 2] = w[j] * cq.gb;
+    }
+    dbeta_acc += dbeta;
+    st_chunk<C>(sm.o[warp], lane * C, ov);
+    st_chunk<3 * C>(sm.o3[warp], lane * 3 * C, o3v);
+    __syncwarp();
+    {
+      float2* o1 = reinterpret_cast<float2*>(d_sdf + ray * S);
+      const float2* s1 = reinterpret_cast<const float2*>(sm.o[warp]);
+#pragma unroll
+      for (int j = 0; j < (C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h1) o1[i] = s1[i];
+      }
+      float2* o3 = reinterpret_cast<float2*>(d_rgb + ray * S * 3);
+      const float2* s3 = reinterpret_cast<const float2*>(sm.o3[warp]);
+#pragma unroll
+      for (int j = 0; j < (3 * C + 1) / 2; ++j) {
+        const int i = lane + 32 * j;
+        if (i < h3) o3[i] = s3[i];
+      }
+    }
+    __syncwarp();
+  }
+  if (d_beta_param) {
+    dbeta_acc = warp_sum(dbeta_acc);
+    if (lane == 0 && dbeta_acc != 0.f) {
+      const float bp = __ldg(beta_param);
+      atomicAdd(d_beta_param, ((bp > 0.f) ? 1.f : ((bp < 0.f) ? -1.f : 0.f)) * dbeta_acc);
+    }
+  }
+}
+
+template <int C, bool HAS_DW>
+static int launch_bwd_lean(const float* z, const float* sdf, const float* rgb, const float* beta_param, float beta_min,
+                           const float* depth_scale, int64_t R, int S, const float* d_rgb_values, const float* d_depth_values,
+                           const float* d_weights, float* d_sdf, float* d_rgb, float* d_beta_param, cudaStream_t st) {
+  static int cap_ctas = 0;
+  const size_t smem = sizeof(LeanBwdSmem<C, HAS_DW>);
+  if (cap_ctas == 0) {
+    int per_sm = 0, sms = 0, dev = 0;
+    SVS_CUDA_OK(cudaFuncSetAttribute(composite_bwd_lean_kernel<C, HAS_DW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, composite_bwd_lean_kernel<C, HAS_DW>, kLeanWarps * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = kNumSMs;
+    cap_ctas = sms * per_sm;
+  }
+  const int64_t blocks = cdiv(R, kLeanWarps);
+  composite_bwd_lean_kernel<C, HAS_DW><<<(int)(blocks < cap_ctas ? blocks : cap_ctas), kLeanWarps * 32, smem, st>>>(
+      z, sdf, rgb, beta_param, beta_min, depth_scale, R, S, d_rgb_values, d_depth_values, d_weights, d_sdf, d_rgb, d_beta_param);
+  return SVS_OK;
+}
+
 // one wave of resident CTAs (grid-stride over rays): a warp's next-ray prefetch then always has a successor
 template <typename K>
 static int comp_grid(K kernel, size_t smem, int64_t R) {
@@ -565,7 +994,17 @@ extern "C" int svs_composite_forward(const float* z, const float* sdf, const flo
   if (R == 0) return SVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_fwd", 0.0, (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (normal_map ? 3 : 0)) + 32), st);
-  if (flags & SVS_COMP_FAST) {
+  const bool lean_ok = flags == SVS_COMP_FAST && rgb && rgb_values && depth_values && depth_scale && !bg_trans && (S & 1) == 0 &&
+                       S > 32 && S <= 256 &&
+                       ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(rgb) |
+                         reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(normal_map ? normals : z)) & 7) == 0;
+  if (lean_ok) {
+    if (normal_map) {
+      DISPATCH_C(S, (launch_fwd_lean<C, true>(z, sdf, rgb, normals, beta_param, beta_min, depth_scale, R, S, weights, rgb_values, depth_values, normal_map, st)));
+    } else {
+      DISPATCH_C(S, (launch_fwd_lean<C, false>(z, sdf, rgb, normals, beta_param, beta_min, depth_scale, R, S, weights, rgb_values, depth_values, normal_map, st)));
+    }
+  } else if (flags & SVS_COMP_FAST) {
     if (normal_map) {
       DISPATCH_C(S, (composite_fwd_kernel<C, true, 3><<<comp_grid(composite_fwd_kernel<C, true, 3>, sizeof(CompSmem<C, 3>), R), kCompWarps * 32, sizeof(CompSmem<C, 3>), st>>>(
                         z, sdf, rgb, normals, beta_param, beta_min, depth_scale, z_max, R, S, flags, weights,
@@ -605,7 +1044,18 @@ extern "C" int svs_composite_backward(const float* z, const float* sdf, const fl
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps("composite_bwd", 0.0,
                (double)R * (4.0 * S * (3 + (rgb ? 3 : 0) + (d_weights ? 1 : 0) + (d_rgb ? 3 : 0)) + 32), st);
-  if (flags & SVS_COMP_FAST) {
+  const bool lean_ok = flags == SVS_COMP_FAST && rgb && d_rgb && d_rgb_values && d_depth_values && depth_scale && (S & 1) == 0 &&
+                       S > 32 && S <= 256 &&
+                       ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(sdf) | reinterpret_cast<uintptr_t>(rgb) |
+                         reinterpret_cast<uintptr_t>(d_sdf) | reinterpret_cast<uintptr_t>(d_rgb) |
+                         reinterpret_cast<uintptr_t>(d_weights ? d_weights : z)) & 7) == 0;
+  if (lean_ok) {
+    if (d_weights) {
+      DISPATCH_C(S, (launch_bwd_lean<C, true>(z, sdf, rgb, beta_param, beta_min, depth_scale, R, S, d_rgb_values, d_depth_values, d_weights, d_sdf, d_rgb, d_beta_param, st)));
+    } else {
+      DISPATCH_C(S, (launch_bwd_lean<C, false>(z, sdf, rgb, beta_param, beta_min, depth_scale, R, S, d_rgb_values, d_depth_values, d_weights, d_sdf, d_rgb, d_beta_param, st)));
+    }
+  } else if (flags & SVS_COMP_FAST) {
     DISPATCH_C(S, (composite_bwd_kernel<C, true, 1><<<comp_grid(composite_bwd_kernel<C, true, 1>, sizeof(CompSmem<C, 1>), R), kCompWarps * 32, sizeof(CompSmem<C, 1>), st>>>(
                       z, sdf, rgb, beta_param, beta_min, depth_scale, z_max, R, S, flags, d_rgb_values,
                       d_depth_values, d_weights, d_bg_trans, d_sdf, d_rgb, d_beta_param)));

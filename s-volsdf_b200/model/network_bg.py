@@ -40,7 +40,7 @@ class VolSDFNetworkBG(nn.Module):
 
     def _comp_flags(self):
         """see VolSDFNetwork._comp_flags: bandwidth-bound compositing arithmetic with the tcgen05 engine"""
-        return L.COMP_FAST if self.implicit_network.engine == L.ENGINE_TC else 0
+        return L.COMP_FAST if self.implicit_network.engine in (L.ENGINE_TC, L.ENGINE_TC_SPLIT) else 0
 
     def forward(self, input, fast=-1):
         if not self.training:
