@@ -43,7 +43,7 @@ struct F3Cfg {
 };
 
 struct F3Bars {
-  uint64_t w_full[kF3MaxSlots], w_empty[kF3MaxSlots], a_ready[kMaxKB * 4], s_free[kMaxKB], acc_full;
+  uint64_t w_full[kF3MaxSlots], w_empty[kF3MaxSlots], a_ready[kMaxKB], s_free[kMaxKB], acc_full;
   uint32_t tmem;
 };
 static_assert(sizeof(F3Bars) <= 512, "barrier block overflows its reservation");
@@ -75,6 +75,23 @@ __device__ __forceinline__ void st_elem_split(uint8_t* a_hi, uint8_t* a_lo, int 
 // Softplus(beta=100)(z) * scale from t = 100 z log2(e): c = ln2/100 * scale (threshold: see softplus_t)
 __device__ __forceinline__ float softplus_t2(float t, float c) {
   return (fmaxf(t, 0.f) + lg2_approx(1.0f + ex2_approx(-fabsf(t)))) * c;
+}
+
+// One 16-column piece of a full softplus layer as ONE basic block: bias, softplus, hi/lo split and the stores, so that
+// the scheduler can overlap the MUFU pipe (2 per element) with the conversion / store instructions of the same piece.
+__device__ __forceinline__ void softplus_piece_split(const uint32_t (&rr)[16], const float* bias_t, float rzk, float csp,
+                                                     uint8_t* blk_hi, uint8_t* blk_lo, int m, int cq) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias_t);
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = __ldg(b4 + i);
+    o[4 * i + 0] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 0]), rzk, b.x), csp);
+    o[4 * i + 1] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 1]), rzk, b.y), csp);
+    o[4 * i + 2] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 2]), rzk, b.z), csp);
+    o[4 * i + 3] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 3]), rzk, b.w), csp);
+  }
+  st_row16_split(blk_hi, blk_lo, m, cq, o);
 }
 
 __device__ __forceinline__ float pe_eval_precise(const float (&xv)[4], PeEntry e) {
@@ -126,7 +143,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < kMaxKB * 4; ++i) mbar_init(&bars->a_ready[i], kPieceWarps);
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->a_ready[i], kF3NW);   // one per 64-column block: every epilogue warp writes one 16-column piece of it
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->s_free[i], 1);
     mbar_init(&bars->acc_full, 1);
     mbar_fence_init();
@@ -185,15 +202,13 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               const uint32_t use = seq / NS;
               ++seq;
               mbar_wait(&bars->w_full[slot], use & 1);
+              mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+              a_par ^= 1u << kb;
+              tc_fence_after();
               const uint32_t b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int bi = kb * 4 + j;
-                mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
-                a_par ^= 1u << bi;
-                tc_fence_after();
+              for (int j = 0; j < 4; ++j)
                 umma_f16(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
-              }
               umma_commit(&bars->w_empty[slot]);
             }
             {   // A_lo(kb) x W_hi(kb); the last block stays for the first main-term block
@@ -235,10 +250,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     if (lane == 0 && any_save) {
       uint32_t a_par = 0;
       auto consume = [&](int kb) {
-        for (int bi = kb * 4; bi < kb * 4 + 4; ++bi) {
-          mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
-          a_par ^= 1u << bi;
-        }
+        mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+        a_par ^= 1u << kb;
       };
       for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
         for (int b = 0; b < ch.pro_kb; ++b) consume(b);
@@ -312,7 +325,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           st_row16_split(sAhi + b * kBlk, sAlo + b * kBlk, m, pc & 3, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
+          if (lane == 0) mbar_arrive(&bars->a_ready[b]);
         }
       } else {
         // A = [feat (F columns) | points(3) if idr, PE(view), normals(3) if idr].  Features are fp32 row-major: warp ew
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         fence_proxy_async();
         named_bar_sync(1, kF3NW * 32);
         if (lane == 0)
-          for (int pc = cg; pc < ch.pro_kb * 4; pc += NCG) mbar_arrive(&bars->a_ready[pc]);
+          for (int b = 0; b < ch.pro_kb; ++b) mbar_arrive(&bars->a_ready[b]);
       }
       for (int b = 0; b < ch.pro_kb; ++b) fgen ^= 1u << b;
 
@@ -397,7 +410,33 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
-            for (int pc = cg; pc < ch.st[s + 1].KB * 4; pc += NCG) mbar_arrive(&bars->a_ready[pc]);
+            for (int b = 0; b < ch.st[s + 1].KB; ++b) mbar_arrive(&bars->a_ready[b]);
+        }
+        if constexpr (MODE == kF2Sdf) {
+          if (st.epi == EP_SOFTPLUS && st.n_valid == 256 && st.next_kb == 4) {
+            // hot path (7 of the 8 hidden layers): 4 pieces per warp, unrolled with two alternating register sets for
+            // the TMEM loads (no copies), every piece one basic block
+            uint32_t ra[16], rb[16];
+            const uint32_t tm0 = tm_acc + (uint32_t)(cg * 16);
+            tmem_ld_32x16(tm0, ra);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (any_save) mbar_wait(&bars->s_free[k], ((fgen >> k) & 1) ^ 1);
+              tmem_ld_wait();
+              if (k < 3) {
+                if (k & 1) tmem_ld_32x16(tm0 + (uint32_t)((k + 1) * 64), ra);
+                else tmem_ld_32x16(tm0 + (uint32_t)((k + 1) * 64), rb);
+              }
+              if (k & 1) softplus_piece_split(rb, st.bias_t + k * 64 + cg * 16, rzk, csp, sAhi + k * kBlk, sAlo + k * kBlk, m, cg);
+              else softplus_piece_split(ra, st.bias_t + k * 64 + cg * 16, rzk, csp, sAhi + k * kBlk, sAlo + k * kBlk, m, cg);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars->a_ready[k]);
+            }
+            fgen ^= 15u;
+            tc_fence_before();
+            continue;
+          }
         }
         const int npc = max((st.n_pad + 15) >> 4, st.next_kb * 4);
         uint32_t rr[16];
@@ -508,7 +547,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
+            if (lane == 0) mbar_arrive(&bars->a_ready[c]);
           }
         }
         if (writes_a)
