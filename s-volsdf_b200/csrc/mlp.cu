@@ -395,6 +395,18 @@ static bool engine_ok(int engine) { return engine == SVS_ENGINE_FP32 || engine =
 static bool is_tc(int engine) { return engine == SVS_ENGINE_TC || engine == SVS_ENGINE_TC_SPLIT; }
 static bool is_split(int engine) { return engine == SVS_ENGINE_TC_SPLIT; }
 
+#if defined(SVS_F3_TRACE) || defined(SVS_CHAIN_TRACE)
+// measurement builds only: copies the trace of tc_fwd3_kernel out and resets it (tools/f3_trace.py)
+extern "C" int svs_dbg_f3_trace(long long* out, int n) {
+  cudaDeviceSynchronize();
+  if (n > 16384) n = 16384;
+  cudaMemcpyFromSymbol(out, svs::tc::g_f3_trace, sizeof(long long) * n);
+  static long long zeros[16384];
+  cudaMemcpyToSymbol(svs::tc::g_f3_trace, zeros, sizeof(zeros));
+  return n;
+}
+#endif
+
 extern "C" int64_t svs_mlp_wbuf_floats(const svs_mlp_desc* d, int engine) {
   Layout lo;
   if (make_layout(d, &lo) != SVS_OK || !engine_ok(engine)) return -1;

@@ -39,6 +39,7 @@ constexpr int kMaxKB = 5;             // widest A operand: 320 columns
 constexpr int kWSlots = 2, kWSlot = 32768;
 constexpr int kXSlots = 3, kXSlot = 16384;   // aux ring; chains with two aux tiles per block use a 4th slot (kXSlotsMax)
 constexpr int kXSlotsMax = 4;                // ... that overlays the stash region (unused by those chains)
+constexpr int kAuxAhead = 0;                 // aux blocks pulled into L2 ahead of the ring (0: off, see the aux producer)
 constexpr int kCtrlThreads = 128;     // 4 control warps; then NW epilogue warps (16 or 24, template parameter)
 constexpr int kPieceWarps = 4;        // a 16-column piece of a block is written by 4 warps (one per TMEM lane quarter)
 constexpr int kChunkWarps = 16;       // ... and a 64-column block by 16
@@ -138,6 +139,34 @@ struct TcChain {
   const uint32_t* amax; float amax_target;
 };
 
+#if defined(SVS_F3_TRACE) || defined(SVS_CHAIN_TRACE)
+// clock64 trace of CTA 0, third tile (measurement builds only; read with tools/f3_trace.py).  Every tracing thread owns a
+// 1024-entry lane of the buffer (plain stores, no atomics: an event costs a clock read and a store).
+__device__ unsigned long long g_f3_trace[16384];
+__device__ unsigned int g_f3_trace_n;
+__device__ __forceinline__ void f3_ev(bool on, int lane_id, uint32_t& n, int tag, int a, int b) {
+  if (!on || n >= 1024u) return;
+  g_f3_trace[lane_id * 1024 + n++] = ((unsigned long long)clock64() & 0xFFFFFFFFFFull) | ((unsigned long long)tag << 56) |
+                                     ((unsigned long long)(a & 255) << 48) | ((unsigned long long)(b & 255) << 40);
+}
+#endif
+#ifdef SVS_F3_TRACE
+#define F3_EV(on, tag, a, b) f3_ev(on, trace_lane, trace_n, tag, a, b)
+#else
+#define F3_EV(on, tag, a, b)
+#endif
+#ifndef SVS_CTRL_SLEEP
+#define SVS_CTRL_SLEEP 0   // ns between barrier probes of the producer / store lanes (0: tight try_wait loop)
+#endif
+#ifndef SVS_CHAIN_EXP
+#define SVS_CHAIN_EXP 0   // measurement builds only: 1 no weight copies, 2 no aux copies, 4 no tile saves, 8 no MMA
+#endif
+#ifdef SVS_CHAIN_TRACE
+#define TC_EV(on, tag, a, b) f3_ev(on, trace_lane, trace_n, tag, a, b)
+#else
+#define TC_EV(on, tag, a, b)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -160,6 +189,15 @@ __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+
+// barrier wait of the producer / store lanes: these single-lane warps share a scheduler with four epilogue warps each
+__device__ __forceinline__ void mbar_wait_ctrl(uint64_t* bar, uint32_t parity) {
+  if (SVS_CTRL_SLEEP > 0) {
+    while (!mbar_try(bar, parity)) __nanosleep(SVS_CTRL_SLEEP);
+  } else {
+    mbar_wait(bar, parity);
+  }
 }
 
 // power-of-two scale that brings the largest upstream gradient (|.| max as float bits in *amax) to ~target
@@ -284,6 +322,11 @@ __host__ __device__ constexpr uint32_t epi_bit(int e) { return 1u << e; }
 template <uint32_t EPI, int PRO, int NW>
 __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(const __grid_constant__ TcChain ch) {
   constexpr int kThreads = kCtrlThreads + NW * 32, kEpiThreads = NW * 32, NCG = NW / 4;   // NCG column groups
+#ifdef SVS_CHAIN_TRACE
+  constexpr bool kTraceThis = PRO == SVS_CHAIN_TRACE;   // measurement builds: -DSVS_CHAIN_TRACE=<prologue id of the chain to trace>
+#else
+  constexpr bool kTraceThis = false;
+#endif
   static_assert(NW % 4 == 0 && NCG >= 4, "every block needs 4 distinct column groups");
   static_assert(NW == 16 || (PRO != PRO_DY && (EPI & epi_bit(EP_DFEAT)) == 0), "row-ownership passes assume 16 epilogue warps x 8 rows");
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -327,7 +370,8 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           for (int kb = 0; kb < st.KB; ++kb, ++seq) {
             const int slot = seq % kWSlots;
             const uint32_t use = seq / kWSlots;
-            mbar_wait(&bars->w_empty[slot], (use & 1) ^ 1);
+            mbar_wait_ctrl(&bars->w_empty[slot], (use & 1) ^ 1);
+            if (SVS_CHAIN_EXP & 1) { mbar_arrive(&bars->w_full[slot]); continue; }
             mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
             bulk_g2s(sW + slot * kWSlot, st.w + (size_t)kb * bytes, bytes, &bars->w_full[slot]);
           }
@@ -338,29 +382,38 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
     // ===== MMA issuer: block kb of step s is issued as soon as the epilogue of step s-1 has rewritten it =====
     if (lane == 0) {
       uint32_t seq = 0, n_step = 0, a_par = 0;
+#ifdef SVS_CHAIN_TRACE
+      const int trace_lane = 0;
+      uint32_t trace_n = 0;
+#endif
       for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
         for (int s = 0; s < ch.n_steps; ++s, ++n_step) {
           const TcStep& st = ch.st[s];
           const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
           const uint32_t acc = tmem + (n_step & 1) * 256;
+          TC_EV(tr, 1, s, 0);
           for (int kb = 0; kb < st.KB; ++kb, ++seq) {
             const int slot = seq % kWSlots;
             const uint32_t use = seq / kWSlots;
             mbar_wait(&bars->w_full[slot], use & 1);
+            TC_EV(tr, 2, s, kb);
             const uint32_t a0 = smem_u32(sA + kb * kBlk), b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               // k-step j multiplies columns [64 kb + 16 j, +16): exactly what the 4 epilogue warps with cq == j wrote
               const int bi = kb * 4 + j;
               mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
+              TC_EV(tr, 3, s, bi);
               a_par ^= 1u << bi;
               tc_fence_after();
-              umma_f16(acc, make_smem_desc(a0 + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc,
-                       (kb | j) != 0);
+              if (!(SVS_CHAIN_EXP & 8))
+                umma_f16(acc, make_smem_desc(a0 + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
             }
             umma_commit(&bars->w_empty[slot]);
           }
           umma_commit(&bars->acc_full);
+          TC_EV(tr, 6, s, 0);
         }
         // a last step that rewrites A publishes blocks nobody multiplies: consume their phases
         const int tail_kb = ch.st[ch.n_steps - 1].next_kb;
@@ -371,28 +424,62 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
       }
     }
   } else if (warp == 2) {
-    // ===== aux producer =====
+    // ===== aux producer: walks the (tile, step, chunk, aux) blocks in the order the epilogue consumes them.  kAuxAhead > 0
+    //       lets a second cursor pull blocks into L2 ahead of the ring (cp.async.bulk.prefetch.L2); measured 8 % SLOWER
+    //       at 12 blocks ahead (the sweeps are bound by their epilogues, tools/chain_trace.py, not by the aux latency):
+    //       off =====
     if (lane == 0) {
       uint32_t seq = 0;
-      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
-        for (int s = 0; s < ch.n_steps; ++s) {
-          const TcStep& st = ch.st[s];
-          if (st.aux1 < 0) continue;
-          const int nchunk = (st.n_pad + 63) >> 6;
-          for (int c = 0; c < nchunk; ++c) {
-            for (int a = 0; a < 2; ++a) {
-              const int id = a ? st.aux2 : st.aux1;
-              if (id < 0) continue;
-              const int slot = seq % XS;
-              const uint32_t use = seq / XS;
-              ++seq;
-              mbar_wait(&bars->x_empty[slot], (use & 1) ^ 1);
-              mbar_arrive_expect_tx(&bars->x_full[slot], kBlk);
-              bulk_g2s(sX + slot * kXSlot, ch.img[id].base + (size_t)t * ch.img[id].tile_bytes + (size_t)c * kBlk, kBlk,
-                       &bars->x_full[slot]);
-            }
-          }
+#ifdef SVS_CHAIN_TRACE
+      const int trace_lane = 4;
+      uint32_t trace_n = 0;
+#endif
+      struct Cur {
+        int t, s, c, a;
+      };
+      auto valid = [&](const Cur& k) { return k.t < ch.n_tiles; };
+      auto id_of = [&](const Cur& k) { return k.a ? ch.st[k.s].aux2 : ch.st[k.s].aux1; };
+      // moves to the next existing block at or after k (k itself if it exists)
+      auto settle = [&](Cur& k) {
+        while (k.t < ch.n_tiles) {
+          if (k.s >= ch.n_steps) { k.t += gridDim.x; k.s = 0; k.c = 0; k.a = 0; continue; }
+          const TcStep& st = ch.st[k.s];
+          if (st.aux1 < 0 || k.c >= ((st.n_pad + 63) >> 6)) { ++k.s; k.c = 0; k.a = 0; continue; }
+          if (k.a > 1) { ++k.c; k.a = 0; continue; }
+          if (id_of(k) < 0) { ++k.a; continue; }
+          return;
         }
+      };
+      auto src_of = [&](const Cur& k) {
+        const int id = id_of(k);
+        return ch.img[id].base + (size_t)k.t * ch.img[id].tile_bytes + (size_t)k.c * kBlk;
+      };
+      Cur ld{(int)blockIdx.x, 0, 0, 0}, pf{(int)blockIdx.x, 0, 0, 0};
+      settle(ld);
+      settle(pf);
+      for (int i = 0; kAuxAhead > 0 && i < kAuxAhead && valid(pf); ++i) {
+        if (i >= XS) bulk_prefetch_l2(src_of(pf), kBlk);   // the first XS blocks go straight into the ring
+        ++pf.a;
+        settle(pf);
+      }
+      while (valid(ld)) {
+        if (kAuxAhead > 0 && valid(pf)) {
+          bulk_prefetch_l2(src_of(pf), kBlk);
+          ++pf.a;
+          settle(pf);
+        }
+        const int slot = seq % XS;
+        const uint32_t use = seq / XS;
+        ++seq;
+        mbar_wait_ctrl(&bars->x_empty[slot], (use & 1) ^ 1);
+        TC_EV(kTraceThis && blockIdx.x == 0 && ld.t == 2 * (int)gridDim.x, 20, ld.s, ld.c * 2 + ld.a);
+        if (SVS_CHAIN_EXP & 2) mbar_arrive(&bars->x_full[slot]);
+        else {
+          mbar_arrive_expect_tx(&bars->x_full[slot], kBlk);
+          bulk_g2s(sX + slot * kXSlot, src_of(ld), kBlk, &bars->x_full[slot]);
+        }
+        ++ld.a;
+        settle(ld);
       }
     }
   } else if (warp == 3) {
@@ -400,9 +487,13 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
     //       back to the epilogue (s_free) once the async proxy has read them =====
     if (lane == 0) {
       uint32_t a_par = 0, z_par = 0, xs_seq = 0;
+#ifdef SVS_CHAIN_TRACE
+      const int trace_lane = 5;
+      uint32_t trace_n = 0;
+#endif
       auto consume = [&](int kb) {
         for (int bi = kb * 4; bi < kb * 4 + 4; ++bi) {
-          mbar_wait(&bars->a_ready[bi], (a_par >> bi) & 1);
+          mbar_wait_ctrl(&bars->a_ready[bi], (a_par >> bi) & 1);
           a_par ^= 1u << bi;
         }
       };
@@ -414,6 +505,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           bulk_wait_read<0>();
         }
         for (int b = 0; b < ch.pro_kb; ++b) mbar_arrive(&bars->s_free[b]);
+        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
         for (int s = 0; s < ch.n_steps; ++s) {
           const TcStep& st = ch.st[s];
           if (st.next_kb > 0) {
@@ -422,20 +514,23 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
                 // zeta block c was written over the U block in its aux slot by all epilogue warps
                 const int slot2 = (xs_seq + 1) % XS;
                 xs_seq += 2;
-                mbar_wait(&bars->z_ready[slot2], (z_par >> slot2) & 1);
+                mbar_wait_ctrl(&bars->z_ready[slot2], (z_par >> slot2) & 1);
                 z_par ^= 1u << slot2;
-                bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk, sX + slot2 * kXSlot, kBlk);
+                if (!(SVS_CHAIN_EXP & 4))
+                  bulk_s2g(ch.img[st.out2].base + (size_t)t * ch.img[st.out2].tile_bytes + (size_t)c * kBlk, sX + slot2 * kXSlot, kBlk);
                 bulk_commit();
                 bulk_wait_read<0>();
                 mbar_arrive_n(&bars->x_empty[slot2], kChunkWarps);
               }
               consume(c);
-              if (st.save >= 0) {
+              TC_EV(tr, 30, s, c);
+              if (st.save >= 0 && !(SVS_CHAIN_EXP & 4)) {
                 bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes + (size_t)c * kBlk, sA + c * kBlk, kBlk);
                 bulk_commit();
               }
             }
             if (st.save >= 0) bulk_wait_read<0>();
+            TC_EV(tr, 31, s, 0);
             for (int c = 0; c < st.next_kb; ++c) mbar_arrive(&bars->s_free[c]);
           } else if (s + 1 < ch.n_steps) {
             for (int c = 0; c < ch.st[s + 1].KB; ++c) consume(c);
@@ -453,6 +548,10 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
     const bool leader = (et == 0);
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t n_acc = 0, xseq = 0, n_load = 0, fgen = 0;   // fgen: parity of the write generation of each A block
+#ifdef SVS_CHAIN_TRACE
+    const int trace_lane = 1 + (ew == 0 ? 0 : (ew == 5 ? 1 : 2));
+    uint32_t trace_n = 0;
+#endif
     const float gs = grad_scale(ch.amax, ch.amax_target);
     const float inv_gs = 1.0f / gs;
     const int pe_w = ch.d_in * (1 + 2 * ch.n_freqs);
@@ -670,6 +769,8 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         mbar_wait(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
+        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 5 || ew == 15);
+        TC_EV(tr, 7, s, ew);
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
@@ -686,6 +787,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           const int c = pc >> 2, cq = pc & 3;
           const int col0 = pc * 16;
           float acc[16];
+          TC_EV(tr, 8, s, pc);
           if (col0 < st.n_pad) {
             tmem_ld_wait();
 #pragma unroll
@@ -694,6 +796,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
           }
+          TC_EV(tr, 9, s, pc);
           if (col0 + NCG * 16 < st.n_pad) tmem_ld_32x16(tm_acc + (uint32_t)(col0 + NCG * 16), rr);
           // aux tiles of this chunk
           uint32_t a1[8], a2[8];   // aux values stay packed (fp16 pairs) until they are used: 16 registers less
@@ -713,6 +816,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
               }
             }
           }
+          TC_EV(tr, 13, s, pc);
           float o[16];
           const bool full = col0 + 16 <= st.n_valid;   // no pad columns in this thread's 16
           if ((EPI & epi_bit(EP_SOFTPLUS)) && st.epi == EP_SOFTPLUS) {
@@ -877,12 +981,15 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             }
           }
           if (writes_a && c < st.next_kb) {
+            TC_EV(tr, 10, s, pc);
             mbar_wait(&bars->s_free[c], ((fgen >> c) & 1) ^ 1);   // the previous generation of this block has been saved
+            TC_EV(tr, 14, s, pc);
             st_row16(sA + c * kBlk, m, cq, o);
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
+            TC_EV(tr, 12, s, pc);
             if (st.colsum >= 0) {
               float cs = warp_colsum16(o, lane);
               if (lane < 16) atomicAdd(&colsum[st.colsum * kColsumW + col0 + lane], cs);

@@ -226,12 +226,10 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
     ch.amax_target = amax_target;
     ch.prologue = PRO_DY;
     ch.pro_kb = kb_of(lo.out[L - 1]);
-    int ni = 0, nc = 0;
+    int ni = 0;
     ch.img[ni] = timg(bw.DY);
     ch.pro_save = ni++;
-    ch.pro_colsum = nc;
-    ch.colsum_out[nc] = dwbuf + lo.boff[L - 1];
-    ch.colsum_n[nc++] = lo.out[L - 1];
+    // bias gradients = column sums of dy / dz_l: taken by the weight-gradient kernel from the saved images (job_bias)
     for (int l = L - 1; l >= 1; --l) {
       TcStep s = make_step(reg + wi.bwd[l], nullptr, wi.bwd_kb[l], wi.bwd_npad[l], lo.out[l - 1], EP_BACKWARD);
       if (l == lo.skip) {
@@ -247,9 +245,6 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
       ch.img[ni] = timg(bw.DZ[l - 1]);
       s.save = ni++;
       s.next_kb = kb_of(lo.out[l - 1]);
-      s.colsum = nc;
-      ch.colsum_out[nc] = dwbuf + lo.boff[l - 1];
-      ch.colsum_n[nc++] = lo.out[l - 1];
       ch.st[ch.n_steps++] = s;
     }
     SVS_TRY(launch_chain(ch, "mlp_tc_sdf_bwd", chain_flops(ch), 0.0, st));
@@ -263,6 +258,7 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
       DwJob j = make_job(dwbuf + lo.woff[l], lo.ldi[l], lo.out[l], lo.in[l]);
       if (have_tangent) job_pair(&j, sv.U[l], bw.Q[l]);
       job_pair(&j, bw.DZ[l], l ? sv.H[l] : sv.A0);
+      job_bias(&j, dwbuf + lo.boff[l]);
       j.x_blk0 = 0;
       j.n_mblk = (int)cdiv(lo.out[l], 128);
       j.y_blk0 = 0;
@@ -274,12 +270,14 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
       const int n_main = lo.out[l] < 256 ? lo.out[l] : 256;
       DwJob j = make_job(dwbuf + lo.woff[l], lo.ldi[l], n_main, lo.in[l]);
       job_pair(&j, bw.DY, sv.H[l]);
+      job_bias(&j, dwbuf + lo.boff[l]);
       j.n_mblk = (int)cdiv(n_main, 128);
       j.n_yblk = j.y_kb;
       prm.job[prm.n_jobs++] = j;
       if (lo.out[l] > 256) {
         DwJob k = make_job(dwbuf + lo.woff[l] + (size_t)256 * lo.ldi[l], lo.ldi[l], lo.out[l] - 256, lo.in[l]);
         job_pair(&k, bw.DY, sv.H[l]);
+        job_bias(&k, dwbuf + lo.boff[l] + 256);
         k.x_blk0 = 4;
         k.n_mblk = 1;
         k.n_yblk = k.y_kb;
@@ -362,12 +360,9 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
     ch.ld_dfeat = ld_dfeat;
     ch.prologue = PRO_SIGMOID_BWD;
     ch.pro_kb = 1;
-    int ni = 0, nc = 0;
+    int ni = 0;
     ch.img[ni] = timg(rw.DZ[L - 1]);
     ch.pro_save = ni++;
-    ch.pro_colsum = nc;
-    ch.colsum_out[nc] = dwbuf + lo.boff[L - 1];
-    ch.colsum_n[nc++] = lo.out[L - 1];
     for (int l = L - 1; l >= 1; --l) {
       TcStep s = make_step(reg + wi.bwd[l], nullptr, wi.bwd_kb[l], wi.bwd_npad[l], lo.in[l], EP_RELU_BWD);
       ch.img[ni] = timg(sv.H[l]);
@@ -375,9 +370,6 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
       ch.img[ni] = timg(rw.DZ[l - 1]);
       s.save = ni++;
       s.next_kb = kb_of(lo.in[l]);
-      s.colsum = nc;
-      ch.colsum_out[nc] = dwbuf + lo.boff[l - 1];
-      ch.colsum_n[nc++] = lo.out[l - 1];
       ch.st[ch.n_steps++] = s;
     }
     if (d_feat) ch.st[ch.n_steps++] = make_step(reg + wi.bwd[0], nullptr, wi.bwd_kb[0], wi.bwd_npad[0], wi.F, EP_DFEAT);
@@ -397,6 +389,7 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
       // layer 0: the saved input is [features | other columns]; W columns are [other | features]
       DwJob a = make_job(dwbuf + lo.woff[0], lo.ldi[0], lo.out[0], wi.F);
       job_pair(&a, rw.DZ[0], sv.RIN);
+      job_bias(&a, dwbuf + lo.boff[0]);
       a.n_mblk = (int)cdiv(lo.out[0], 128);
       a.y_blk0 = 0;
       a.n_yblk = wi.F / 64;
@@ -412,6 +405,7 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
     for (int l = 1; l < L; ++l) {
       DwJob j = make_job(dwbuf + lo.woff[l], lo.ldi[l], lo.out[l], lo.in[l]);
       job_pair(&j, rw.DZ[l], sv.H[l]);
+      job_bias(&j, dwbuf + lo.boff[l]);
       j.n_mblk = (int)cdiv(lo.out[l], 128);
       j.n_yblk = j.y_kb;
       prm.job[prm.n_jobs++] = j;

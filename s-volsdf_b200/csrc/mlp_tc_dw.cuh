@@ -7,6 +7,10 @@
 // One CTA owns one (job, split): it keeps the fp32 accumulators (up to 2 x 128 x 256 = all 512 TMEM columns) over
 // all of its tiles and both (X, Y) pairs of the job (tangent-sweep pair and backward pair share dW_l), then adds its
 // partial result into the fp32 gradient buffer with vector reductions (REDG.F32x4).
+// The bias gradients db_l = sum_p dz_l[p, :] ride along: epilogue warp 0, idle until the accumulators are complete, adds
+// up the columns of the X slices of the backward pair while the slices wait in the ring (a lane per column pair, fp32
+// partial sums in registers over all tiles of the CTA), so the chains' epilogues carry no column reductions (they cost
+// a quarter of the backward sweep's epilogue: shuffles + shared-memory CAS loops).
 #pragma once
 #include "mlp_tc.cuh"
 
@@ -31,6 +35,8 @@ struct DwJob {
   int32_t ldw, n_rows, n_cols;    // valid rows (X columns) / cols (Y columns) of this job's slab
   int32_t col_shift;              // output column = n + col_shift (rendering layer 0: features sit after 15 columns)
   int32_t unit0, n_split;         // CTAs [unit0, unit0 + n_split) work on this job
+  float* bias;                    // != nullptr: db[n] += sum_p X[p, n] of pair `bias_pair` (the bias gradient of the layer:
+  int32_t bias_pair;              //   column sums of dz_l / dy, taken from the X slices while they sit in shared memory)
 };
 
 struct DwParams {
@@ -58,7 +64,8 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
   for (int i = threadIdx.x * 16; i < kDwStages * kDwStageBytes; i += blockDim.x * 16)
     *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kDwStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    // a stage is free again when its MMAs have completed and, in jobs with a bias, the four summing warps have read it
+    for (int i = 0; i < kDwStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], jb.bias ? 5 : 1); }
     mbar_init(&bars->acc_full, 1);
     mbar_fence_init();
   }
@@ -126,10 +133,55 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ D
           }
         }
         umma_commit(&bars->empty[slot]);
+        // jobs with a bias: the four summing warps also release the stages of the backward pair; stand in for them elsewhere
+        if (jb.bias && (seq / (kTile / kDwRows)) % jb.n_pairs != jb.bias_pair) mbar_arrive_n(&bars->empty[slot], 4);
       }
       umma_commit(&bars->acc_full);
     }
   } else if (warp < 4) {
+    if (jb.bias && n_stage_total > 0) {
+      // ===== bias gradient: column sums of X block `warp` of every stage of the backward pair =====
+      // lane = row of the 32-row slice; logical 16-byte chunk j of row r sits at chunk position j ^ (r & 7): the 8 lanes of a
+      // quarter warp read 8 different positions (conflict-free) and every lane keeps static accumulator indices.  Only
+      // warp 0 probes the `full` barrier (every probing warp costs the ring ~1 %: measured); it releases the other three
+      // through a named barrier.
+      const bool mine = warp < nx && jb.x_blk0 + warp < jb.x_kb;
+      float cs[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) cs[i] = 0.f;
+      const int per_tile = kTile / kDwRows;
+      for (int seq = 0; seq < n_stage_total; ++seq) {
+        const int slot = seq % kDwStages;
+        const uint32_t use = seq / kDwStages;
+        const int pr = (seq / per_tile) % jb.n_pairs;
+        if (pr != jb.bias_pair) continue;   // stages of the other pair are released by the MMA commit alone (see `empty`)
+        if (warp == 0) mbar_wait(&bars->full[slot], use & 1);
+        named_bar_sync(1, 128);
+        if (mine) {
+          const uint8_t* row = smem + slot * kDwStageBytes + warp * kDwSlice + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(row + ((j ^ (lane & 7)) << 4));
+            float2 f;
+            f = unpack_h2(u.x); cs[8 * j + 0] += f.x; cs[8 * j + 1] += f.y;
+            f = unpack_h2(u.y); cs[8 * j + 2] += f.x; cs[8 * j + 3] += f.y;
+            f = unpack_h2(u.z); cs[8 * j + 4] += f.x; cs[8 * j + 5] += f.y;
+            f = unpack_h2(u.w); cs[8 * j + 6] += f.x; cs[8 * j + 7] += f.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->empty[slot]);
+      }
+      if (mine) {
+        const float inv_gs = 1.0f / grad_scale(prm.amax, prm.amax_target);
+        const int col0 = warp * 64;   // column of this job's slab
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float v = warp_sum(cs[i]);
+          if (lane == (i & 31) && col0 + i < jb.n_rows) atomicAdd(jb.bias + col0 + i, v * inv_gs);
+        }
+      }
+    }
     // ===== epilogue: TMEM -> fp32 reductions into dW =====
     if (n_stage_total > 0) {
       mbar_wait(&bars->acc_full, 0);

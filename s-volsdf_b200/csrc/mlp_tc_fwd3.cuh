@@ -25,6 +25,9 @@
 namespace svs {
 namespace tc {
 
+#ifndef SVS_F3_EXP
+#define SVS_F3_EXP 0   // measurement builds only (tools/f3_exp.sh): 1 no MMA, 2 no MUFU, 4 no A stores, 8 no weight copies, 16 idle epilogue
+#endif
 constexpr int kF3NW = 16;
 constexpr int kF3Threads = kCtrlThreads + kF3NW * 32;
 constexpr int kF3MaxSlots = 3;
@@ -49,6 +52,9 @@ struct F3Bars {
 static_assert(sizeof(F3Bars) <= 512, "barrier block overflows its reservation");
 
 // hi / lo halves of 16 consecutive columns of row m
+__device__ __forceinline__ void f3_umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  if (!(SVS_F3_EXP & 1)) umma_f16(d, a, b, idesc, accum);
+}
 __device__ __forceinline__ void st_row16_split(uint8_t* blk_hi, uint8_t* blk_lo, int m, int cq, const float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -74,6 +80,7 @@ __device__ __forceinline__ void st_elem_split(uint8_t* a_hi, uint8_t* a_lo, int 
 
 // Softplus(beta=100)(z) * scale from t = 100 z log2(e): c = ln2/100 * scale (threshold: see softplus_t)
 __device__ __forceinline__ float softplus_t2(float t, float c) {
+  if (SVS_F3_EXP & 2) return (fmaxf(t, 0.f) + fmaf(fabsf(t), 1e-3f, 1.0f)) * c;
   return (fmaxf(t, 0.f) + lg2_approx(1.0f + ex2_approx(-fabsf(t)))) * c;
 }
 
@@ -90,6 +97,13 @@ __device__ __forceinline__ void softplus_piece_split(const uint32_t (&rr)[16], c
     o[4 * i + 1] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 1]), rzk, b.y), csp);
     o[4 * i + 2] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 2]), rzk, b.z), csp);
     o[4 * i + 3] = softplus_t2(fmaf(__uint_as_float(rr[4 * i + 3]), rzk, b.w), csp);
+  }
+  if (SVS_F3_EXP & 4) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc += o[i];
+    if (acc == 123.456f) blk_hi[m] = 1;
+    return;
   }
   st_row16_split(blk_hi, blk_lo, m, cq, o);
 }
@@ -164,6 +178,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         const uint32_t use = seq / NS;
         ++seq;
         mbar_wait(&bars->w_empty[slot], (use & 1) ^ 1);
+        if (SVS_F3_EXP & 8) { mbar_arrive(&bars->w_full[slot]); return; }
         mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
         bulk_g2s(sW + slot * kWSlot, src, bytes, &bars->w_full[slot]);
       };
@@ -190,11 +205,17 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     //       the previous step at 16-column granularity. =====
     if (lane == 0) {
       uint32_t seq = 0, n_step = 0, a_par = 0;
+#ifdef SVS_F3_TRACE
+      const int trace_lane = 0;
+      uint32_t trace_n = 0;
+#endif
       for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
         for (int s = 0; s < ch.n_steps; ++s, ++n_step) {
           const TcStep& st = ch.st[s];
           const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
           const uint32_t acc = tmem + (n_step & 1) * 256;
+          const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x;
+          F3_EV(tr, 1, s, 0);
           for (int kb = 0; kb < st.KB; ++kb) {
             const uint32_t ah = smem_u32(sAhi + kb * kBlk), al = smem_u32(sAlo + kb * kBlk);
             {   // A_hi(kb) x W_lo(kb)
@@ -202,13 +223,15 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               const uint32_t use = seq / NS;
               ++seq;
               mbar_wait(&bars->w_full[slot], use & 1);
+              F3_EV(tr, 2, s, kb);
               mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+              F3_EV(tr, 3, s, kb);
               a_par ^= 1u << kb;
               tc_fence_after();
               const uint32_t b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                umma_f16(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
+                f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
               umma_commit(&bars->w_empty[slot]);
             }
             {   // A_lo(kb) x W_hi(kb); the last block stays for the first main-term block
@@ -216,15 +239,16 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               const uint32_t use = seq / NS;
               ++seq;
               mbar_wait(&bars->w_full[slot], use & 1);
+              F3_EV(tr, 4, s, kb);
               tc_fence_after();
               const uint32_t b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                umma_f16(acc, make_smem_desc(al + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+                f3_umma(acc, make_smem_desc(al + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
               if (kb == st.KB - 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  umma_f16(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+                  f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
               }
               umma_commit(&bars->w_empty[slot]);
             }
@@ -234,14 +258,16 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             const uint32_t use = seq / NS;
             ++seq;
             mbar_wait(&bars->w_full[slot], use & 1);
+            F3_EV(tr, 5, s, kb);
             tc_fence_after();
             const uint32_t ah = smem_u32(sAhi + kb * kBlk), b0 = smem_u32(sW + slot * kWSlot);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              umma_f16(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+              f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
             umma_commit(&bars->w_empty[slot]);
           }
           umma_commit(&bars->acc_full);
+          F3_EV(tr, 6, s, 0);
         }
       }
     }
@@ -304,6 +330,10 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
       named_bar_sync(1, kF3NW * 32);
     }
     uint32_t n_acc = 0, fgen = 0;
+#ifdef SVS_F3_TRACE
+    const int trace_lane = 1 + (ew == 0 ? 0 : (ew == 5 ? 1 : 2));
+    uint32_t trace_n = 0;
+#endif
 
     for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
       const int64_t p = (int64_t)t * kTile + m;
@@ -407,6 +437,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         mbar_wait_relaxed(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
+        const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 15 || ew == 5);
+        F3_EV(tr, 7, s, ew);
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
@@ -423,15 +455,20 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             for (int k = 0; k < 4; ++k) {
               if (any_save) mbar_wait(&bars->s_free[k], ((fgen >> k) & 1) ^ 1);
               tmem_ld_wait();
+              F3_EV(tr, 9, s, ew * 4 + k);
               if (k < 3) {
                 if (k & 1) tmem_ld_32x16(tm0 + (uint32_t)((k + 1) * 64), ra);
                 else tmem_ld_32x16(tm0 + (uint32_t)((k + 1) * 64), rb);
               }
-              if (k & 1) softplus_piece_split(rb, st.bias_t + k * 64 + cg * 16, rzk, csp, sAhi + k * kBlk, sAlo + k * kBlk, m, cg);
+              if (SVS_F3_EXP & 16) {
+                if ((ra[0] ^ rb[1]) == 0x12345u) sAhi[m] = 1;
+              } else if (k & 1) softplus_piece_split(rb, st.bias_t + k * 64 + cg * 16, rzk, csp, sAhi + k * kBlk, sAlo + k * kBlk, m, cg);
               else softplus_piece_split(ra, st.bias_t + k * 64 + cg * 16, rzk, csp, sAhi + k * kBlk, sAlo + k * kBlk, m, cg);
+              F3_EV(tr, 11, s, ew * 4 + k);
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) mbar_arrive(&bars->a_ready[k]);
+              F3_EV(tr, 12, s, ew * 4 + k);
             }
             fgen ^= 15u;
             tc_fence_before();

@@ -510,6 +510,11 @@ static void job_pair(DwJob* j, const ImgBuf& X, const ImgBuf& Y) {
   j->X[k] = X.base; j->x_tile_bytes[k] = (int64_t)X.kb * kBlk; j->x_kb = X.kb;
   j->Y[k] = Y.base; j->y_tile_bytes[k] = (int64_t)Y.kb * kBlk; j->y_kb = Y.kb;
 }
+// db += column sums of the X image of the pair added last (valid columns: the job's n_rows)
+static void job_bias(DwJob* j, float* bias) {
+  j->bias = bias;
+  j->bias_pair = j->n_pairs - 1;
+}
 
 }  // namespace tc
 }  // namespace svs

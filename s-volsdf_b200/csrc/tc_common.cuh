@@ -95,6 +95,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// global -> L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((uint64_t)src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
