@@ -39,7 +39,6 @@ constexpr int kMaxKB = 5;             // widest A operand: 320 columns
 constexpr int kWSlots = 2, kWSlot = 32768;
 constexpr int kXSlots = 3, kXSlot = 16384;   // aux ring; chains with two aux tiles per block use a 4th slot (kXSlotsMax)
 constexpr int kXSlotsMax = 4;                // ... that overlays the stash region (unused by those chains)
-constexpr int kAuxAhead = 0;                 // aux blocks pulled into L2 ahead of the ring (0: off, see the aux producer)
 constexpr int kCtrlThreads = 128;     // 4 control warps; then NW epilogue warps (16 or 24, template parameter)
 constexpr int kPieceWarps = 4;        // a 16-column piece of a block is written by 4 warps (one per TMEM lane quarter)
 constexpr int kChunkWarps = 16;       // ... and a 64-column block by 16
@@ -129,6 +128,8 @@ struct TcChain {
   const float* yin;            // raw sdf column source for the clamp (reverse / tangent / backward chains)
   float* sdf; float* grad;
   const float* dy; const float* d_sdf; const float* d_grad; int32_t dy_cols;
+  int32_t dy_bulk;             // PRO_DY: the fp32 rows of a tile are staged through the aux ring by bulk copies (dy 16-byte aligned)
+  uint32_t dy_magic;           // ... ceil(2^32 / ldy): row of flat element e = umulhi(e, dy_magic) for e < 2^16
   // rendering net
   const float* points; const float* view; const float* normals; const float* feat; int32_t ld_feat;
   int32_t view_freqs, idr, F;
@@ -316,6 +317,14 @@ struct Bars {   // must fit the 512 bytes reserved at kOffBar
 
 __host__ __device__ constexpr uint32_t epi_bit(int e) { return 1u << e; }
 
+// bytes of tile t's dy rows that travel by bulk copy: whole 16-byte units of the valid rows (the last tile's <= 3 floats
+// behind them are read directly)
+__device__ __forceinline__ uint32_t dy_bulk_bytes(const TcChain& ch, int t) {
+  const int64_t rows = ch.P - (int64_t)t * kTile;
+  const uint32_t nr = rows < kTile ? (uint32_t)rows : (uint32_t)kTile;
+  return (nr * (uint32_t)ch.ldy * 4u) & ~15u;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // the chain kernel; EPI / PRO select which epilogues / prologue are compiled into an instantiation
 // ---------------------------------------------------------------------------------------------------------------
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
       uint32_t trace_n = 0;
 #endif
       for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
-        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
+        [[maybe_unused]] const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
         for (int s = 0; s < ch.n_steps; ++s, ++n_step) {
           const TcStep& st = ch.st[s];
           const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
@@ -424,62 +433,46 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
       }
     }
   } else if (warp == 2) {
-    // ===== aux producer: walks the (tile, step, chunk, aux) blocks in the order the epilogue consumes them.  kAuxAhead > 0
-    //       lets a second cursor pull blocks into L2 ahead of the ring (cp.async.bulk.prefetch.L2); measured 8 % SLOWER
-    //       at 12 blocks ahead (the sweeps are bound by their epilogues, tools/chain_trace.py, not by the aux latency):
-    //       off =====
+    // ===== aux producer: the aux blocks in the order the epilogue consumes them (tile, step, chunk, aux).  A backward
+    //       chain's fp32 dy rows travel through the same ring ahead of step 0 (the 128 rows of a tile are one contiguous
+    //       range of P x ldy: 16 KB pieces, converted to the fp16 operand tile by the epilogue warps).  Pulling blocks into
+    //       L2 ahead of the ring (cp.async.bulk.prefetch.L2, 12 blocks) was measured 8 % SLOWER: the sweeps are bound by
+    //       their epilogues (tools/chain_trace.py), not by the aux latency. =====
     if (lane == 0) {
       uint32_t seq = 0;
 #ifdef SVS_CHAIN_TRACE
       const int trace_lane = 4;
       uint32_t trace_n = 0;
 #endif
-      struct Cur {
-        int t, s, c, a;
-      };
-      auto valid = [&](const Cur& k) { return k.t < ch.n_tiles; };
-      auto id_of = [&](const Cur& k) { return k.a ? ch.st[k.s].aux2 : ch.st[k.s].aux1; };
-      // moves to the next existing block at or after k (k itself if it exists)
-      auto settle = [&](Cur& k) {
-        while (k.t < ch.n_tiles) {
-          if (k.s >= ch.n_steps) { k.t += gridDim.x; k.s = 0; k.c = 0; k.a = 0; continue; }
-          const TcStep& st = ch.st[k.s];
-          if (st.aux1 < 0 || k.c >= ((st.n_pad + 63) >> 6)) { ++k.s; k.c = 0; k.a = 0; continue; }
-          if (k.a > 1) { ++k.c; k.a = 0; continue; }
-          if (id_of(k) < 0) { ++k.a; continue; }
-          return;
-        }
-      };
-      auto src_of = [&](const Cur& k) {
-        const int id = id_of(k);
-        return ch.img[id].base + (size_t)k.t * ch.img[id].tile_bytes + (size_t)k.c * kBlk;
-      };
-      Cur ld{(int)blockIdx.x, 0, 0, 0}, pf{(int)blockIdx.x, 0, 0, 0};
-      settle(ld);
-      settle(pf);
-      for (int i = 0; kAuxAhead > 0 && i < kAuxAhead && valid(pf); ++i) {
-        if (i >= XS) bulk_prefetch_l2(src_of(pf), kBlk);   // the first XS blocks go straight into the ring
-        ++pf.a;
-        settle(pf);
-      }
-      while (valid(ld)) {
-        if (kAuxAhead > 0 && valid(pf)) {
-          bulk_prefetch_l2(src_of(pf), kBlk);
-          ++pf.a;
-          settle(pf);
-        }
+      auto put = [&](const uint8_t* src, uint32_t bytes) {
         const int slot = seq % XS;
         const uint32_t use = seq / XS;
         ++seq;
         mbar_wait_ctrl(&bars->x_empty[slot], (use & 1) ^ 1);
-        TC_EV(kTraceThis && blockIdx.x == 0 && ld.t == 2 * (int)gridDim.x, 20, ld.s, ld.c * 2 + ld.a);
-        if (SVS_CHAIN_EXP & 2) mbar_arrive(&bars->x_full[slot]);
-        else {
-          mbar_arrive_expect_tx(&bars->x_full[slot], kBlk);
-          bulk_g2s(sX + slot * kXSlot, src_of(ld), kBlk, &bars->x_full[slot]);
+        if (SVS_CHAIN_EXP & 2) { mbar_arrive(&bars->x_full[slot]); return; }
+        mbar_arrive_expect_tx(&bars->x_full[slot], bytes);
+        bulk_g2s(sX + slot * kXSlot, src, bytes, &bars->x_full[slot]);
+      };
+      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+        if (PRO == PRO_DY && ch.dy_bulk) {
+          const uint32_t total = dy_bulk_bytes(ch, t);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(ch.dy) + (size_t)t * kTile * ch.ldy * 4;
+          for (uint32_t off = 0; off < total; off += kBlk) put(src + off, total - off < (uint32_t)kBlk ? total - off : (uint32_t)kBlk);
         }
-        ++ld.a;
-        settle(ld);
+        [[maybe_unused]] const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
+        for (int s = 0; s < ch.n_steps; ++s) {
+          const TcStep& st = ch.st[s];
+          if (st.aux1 < 0) continue;
+          const int nchunk = (st.n_pad + 63) >> 6;
+          for (int c = 0; c < nchunk; ++c) {
+            for (int a = 0; a < 2; ++a) {
+              const int id = a ? st.aux2 : st.aux1;
+              if (id < 0) continue;
+              TC_EV(tr, 20, s, c * 2 + a);
+              put(ch.img[id].base + (size_t)t * ch.img[id].tile_bytes + (size_t)c * kBlk, kBlk);
+            }
+          }
+        }
       }
     }
   } else if (warp == 3) {
@@ -505,7 +498,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           bulk_wait_read<0>();
         }
         for (int b = 0; b < ch.pro_kb; ++b) mbar_arrive(&bars->s_free[b]);
-        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
+        [[maybe_unused]] const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x;
         for (int s = 0; s < ch.n_steps; ++s) {
           const TcStep& st = ch.st[s];
           if (st.next_kb > 0) {
@@ -570,9 +563,18 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
       named_bar_sync(1, kEpiThreads);
     }
 
+    if (PRO == PRO_DY && ch.dy_bulk) {
+      // columns ldy .. 64 pro_kb of the dy tile are never written (the staged rows hold ldy floats): zero them once; the
+      // steps only rewrite the first 4 blocks
+      for (int i = et * 16; i < ch.pro_kb * kBlk; i += kEpiThreads * 16) *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+      fence_proxy_async();
+      named_bar_sync(1, kEpiThreads);
+    }
     for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
       const int64_t p = (int64_t)t * kTile + m;
       const bool live = p < ch.P;
+      [[maybe_unused]] const bool trp = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 5 || ew == 15);
+      TC_EV(trp, 40, 0, ew);
       float xv[4] = {0.f, 0.f, 0.f, 0.f};
       if (ch.x && live)
         for (int d = 0; d < ch.d_in; ++d) xv[d] = ch.x[p * ch.d_in + d];
@@ -600,24 +602,61 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
           bulk_g2s(sA, ch.img[ch.pro_img].base + (size_t)t * ch.img[ch.pro_img].tile_bytes, bytes, &bars->a_load);
         }
       }
+      TC_EV(trp, 41, 0, ew);
       named_bar_sync(1, kEpiThreads);
+      TC_EV(trp, 42, 0, ew);
 
       // ---------------- prologue: build the first A operand, one 64-column block at a time ----------------
       if (PRO == PRO_LOAD_ULAST) {
         mbar_wait(&bars->a_load, n_load & 1);
         ++n_load;
+        TC_EV(trp, 43, 0, ew);
       }
       if (PRO == PRO_DY) {
-        // dy is fp32 row-major (P x ldy): warp ew converts rows 8 ew .. 8 ew + 7, a lane reads columns lane, lane + 32,
-        // ... (one 128-byte line per instruction); column 0 (which also takes w * dL/dsdf) is written by the thread
-        // that owns the row.  The pieces are published after all warps are done.
+        // dy is fp32 row-major (P x ldy); column 0 (which also takes w * dL/dsdf) is written by the thread that owns the
+        // row.  The pieces are published after all warps are done.
         for (int b = 0; b < ch.pro_kb; ++b) mbar_wait(&bars->s_free[b], ((fgen >> b) & 1) ^ 1);
+        TC_EV(trp, 43, 0, ew);
         const int64_t trow0 = (int64_t)t * kTile;
         const int ncol = ch.pro_kb * 64;
         float csum[10];
 #pragma unroll
         for (int j = 0; j < 10; ++j) csum[j] = 0.f;
-        for (int rb = 0; rb < 8; rb += 2) {
+        if (ch.dy_bulk) {
+          // the tile's rows arrive as 16 KB pieces of the flat (row, column) array in the aux ring: thread et converts the
+          // floats et, et + 512, ... of a piece (consecutive lanes: consecutive columns of a row, conflict-free both ways)
+          const uint32_t total = dy_bulk_bytes(ch, t);
+          const int64_t rows = ch.P - trow0;
+          const uint32_t n_el = (uint32_t)(rows < kTile ? rows : kTile) * (uint32_t)ch.ldy;   // valid floats of the tile
+          const float* gsrc = ch.dy + trow0 * ch.ldy;
+          for (uint32_t off = 0; off < (uint32_t)(kTile * ch.ldy * 4); off += kBlk) {
+            const uint32_t e0 = off >> 2;
+            int slot = -1;
+            if (off < total) {
+              slot = xseq % XS;
+              mbar_wait(&bars->x_full[slot], (xseq / XS) & 1);
+              ++xseq;
+            }
+            const float* ssrc = reinterpret_cast<const float*>(sX + (slot < 0 ? 0 : slot) * kXSlot);
+#pragma unroll
+            for (int k = 0; k < kBlk / 4 / 512; ++k) {
+              const uint32_t i = (uint32_t)(k * 512 + et), e = e0 + i;
+              if (e >= (uint32_t)(kTile * ch.ldy)) break;
+              float v = 0.f;
+              if (e * 4u + 4u <= total) v = ssrc[i];
+              else if (e < n_el) v = __ldg(gsrc + e);
+              const uint32_t r = __umulhi(e, ch.dy_magic), c = e - r * (uint32_t)ch.ldy;
+              if (c >= 1u && c < (uint32_t)ncol)
+                *reinterpret_cast<__half*>(sA + (c >> 6) * kBlk + chunk_off((int)r, (int)((c & 63) >> 3)) + (c & 7) * 2) =
+                    __float2half_rn(fminf(fmaxf(c < (uint32_t)ch.dy_cols ? v * gs : 0.f, -65504.f), 65504.f));
+            }
+            if (slot >= 0) {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bars->x_empty[slot]);
+            }
+          }
+        }
+        for (int rb = 0; !ch.dy_bulk && rb < 8; rb += 2) {
           float fv[2][10];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -642,6 +681,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             }
           }
         }
+        TC_EV(trp, 44, 0, ew);
         float v0 = 0.f;
         if (cg == 0) {   // one thread per row
           if (live) {
@@ -662,10 +702,12 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             if (lane == 0) atomicAdd(&colsum[ch.pro_colsum * kColsumW], s0);
           }
         }
+        TC_EV(trp, 45, 0, ew);
         fence_proxy_async();
         named_bar_sync(1, kEpiThreads);
         if (lane == 0)
           for (int pc = cg; pc < ch.pro_kb * 4; pc += NCG) mbar_arrive(&bars->a_ready[pc]);
+        TC_EV(trp, 46, 0, ew);
       }
       for (int pc = cg; PRO != PRO_DY && pc < ch.pro_kb * 4; pc += NCG) {
         float v[16];
@@ -754,6 +796,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->a_ready[pc]);
+        TC_EV(trp, 46, 0, pc);
       }
       for (int b = 0; b < ch.pro_kb; ++b) fgen ^= 1u << b;
 
@@ -769,7 +812,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         mbar_wait(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
-        const bool tr = kTraceThis && blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 5 || ew == 15);
+        [[maybe_unused]] const bool tr = kTraceThis && blockIdx.x == 0 && (t == 2 * (int)gridDim.x || t == (int)gridDim.x) && lane == 0 && (ew == 0 || ew == 5 || ew == 15);
         TC_EV(tr, 7, s, ew);
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
@@ -1016,7 +1059,9 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         }
         if ((EPI & epi_bit(EP_PEGRAD)) && st.epi == EP_PEGRAD) {
           // stash now holds p_0 + e for all PE columns of the row: g = J_PE^T (p_0 + e), sphere clamp of sdf and g
+          TC_EV(tr, 47, s, ew);
           named_bar_sync(2, kEpiThreads);
+          TC_EV(tr, 48, s, ew);
           if (cg == 0 && live) {   // the warps that own piece 0 (one thread per row)
             float g[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < pe_w; ++c) {
@@ -1035,7 +1080,9 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             if (ch.grad)
               for (int d = 0; d < ch.d_in; ++d) ch.grad[p * ch.d_in + d] = g[d];
           }
+          TC_EV(tr, 49, s, ew);
           named_bar_sync(2, kEpiThreads);   // the stash is re-zeroed by the next tile's prologue
+          TC_EV(tr, 50, s, ew);
         }
         // every warp advances the ring / generation counters of ALL blocks of the step, also those it did not touch
         if (st.aux1 >= 0) xseq = xbase + (uint32_t)(nchunk_acc * naux);

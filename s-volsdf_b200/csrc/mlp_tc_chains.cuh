@@ -222,6 +222,10 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
     ch.dy = dy;
     ch.d_sdf = d_sdf;
     ch.dy_cols = lo.out[L - 1];
+    // fp32 rows staged through the aux ring by bulk copies (needs 16-byte aligned rows of the tile's flat array)
+    ch.dy_bulk = (dy != nullptr && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (int64_t)kTile * lo.ldy < 65536 &&
+                  lo.ldy <= 64 * kb_of(lo.out[L - 1])) ? 1 : 0;
+    ch.dy_magic = (uint32_t)(0x100000000ull / (uint64_t)lo.ldy) + 1u;
     ch.amax = amax;
     ch.amax_target = amax_target;
     ch.prologue = PRO_DY;
@@ -363,6 +367,11 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
     int ni = 0;
     ch.img[ni] = timg(rw.DZ[L - 1]);
     ch.pro_save = ni++;
+    // bias gradients: the last layer's (n_rgb sums of the prologue's fp32 values, heavily cancelling under an L1 loss) stay
+    // here in fp32; the hidden layers' are column sums of the saved dz images, taken by the weight-gradient kernel
+    ch.pro_colsum = 0;
+    ch.colsum_out[0] = dwbuf + lo.boff[L - 1];
+    ch.colsum_n[0] = lo.out[L - 1];
     for (int l = L - 1; l >= 1; --l) {
       TcStep s = make_step(reg + wi.bwd[l], nullptr, wi.bwd_kb[l], wi.bwd_npad[l], lo.in[l], EP_RELU_BWD);
       ch.img[ni] = timg(sv.H[l]);
@@ -405,7 +414,7 @@ static int render_backward(const svs_mlp_desc* d, const Layout& lo, const float*
     for (int l = 1; l < L; ++l) {
       DwJob j = make_job(dwbuf + lo.woff[l], lo.ldi[l], lo.out[l], lo.in[l]);
       job_pair(&j, rw.DZ[l], sv.H[l]);
-      job_bias(&j, dwbuf + lo.boff[l]);
+      if (l < L - 1) job_bias(&j, dwbuf + lo.boff[l]);
       j.n_mblk = (int)cdiv(lo.out[l], 128);
       j.n_yblk = j.y_kb;
       prm.job[prm.n_jobs++] = j;

@@ -33,7 +33,7 @@ for i in range(n):
 ev.sort()
 t0 = ev[0][0]
 names = {1: 'mma step start', 2: 'mma w_full', 3: 'mma a_ready', 6: 'mma commit acc', 7: 'epi acc_full', 8: 'epi piece start', 9: 'epi tmem ok', 13: 'epi aux ready', 10: 'epi computed',
-         14: 'epi s_free ok', 12: 'epi arrived', 20: 'aux slot free', 30: 'store block ready', 31: 'store read done'}
+         14: 'epi s_free ok', 12: 'epi arrived', 20: 'aux slot free', 40: 'tile top', 41: 'row loads done', 42: 'tile barrier', 43: 'A free / loaded', 44: 'dy rows stored', 45: 'dy col0 done', 46: 'pro piece arrived', 47: 'pegrad pieces done', 48: 'pegrad bar1', 49: 'pegrad computed', 50: 'pegrad bar2', 30: 'store block ready', 31: 'store read done'}
 who = {0: 'MMA', 1: 'E0', 2: 'E5', 3: 'E15', 4: 'AUX', 5: 'ST'}
 print('events', len(ev))
 for t, ln, tag, a, b in ev:
