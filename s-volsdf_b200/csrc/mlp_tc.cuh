@@ -53,8 +53,8 @@ constexpr int kOffA = 0;
 constexpr int kOffW = kOffA + kMaxKB * kBlk;                // 81920
 constexpr int kOffX = kOffW + kWSlots * kWSlot;             // 147456
 constexpr int kOffStash = kOffX + kXSlots * kXSlot;         // 196608
-constexpr int kOffVec = kOffStash + kTile * kStashLd * 4;   // 217088 : bias / row-vector of the step (256 fp32)
-constexpr int kOffVec2 = kOffVec + 1024;                    // second row vector (256 fp32)
+constexpr int kOffVec = kOffStash + kTile * kStashLd * 4;   // 217088 : positional-encoding table (kPeTabCols entries of 8 bytes)
+constexpr int kOffVec2 = kOffVec + 1024;                    // (spare)
 constexpr int kOffColsum = kOffVec2 + 1024;                 // kMaxColsum x 256 fp32 per-CTA column sums
 constexpr int kOffBar = kOffColsum + kMaxColsum * kColsumW * 4;  // 230656
 constexpr int kSmemBytes = kOffBar + 512;                        // 231168 <= 232448 (227 KB)
@@ -266,31 +266,41 @@ __device__ __forceinline__ float softplus100_fast(float z, float c_lo, float c_h
 // sigma'(z) recovered from h = softplus(z): 1 - exp(-100 h)
 __device__ __forceinline__ float dsoftplus_h(float h) { return 1.0f - ex2_approx(-kSpK1 * h); }
 
-__device__ __forceinline__ float pe_col(const float (&xv)[4], int d_in, int n_freqs, int c) {
-  if (c < d_in) return xv[c];
-
-  int t = c - d_in;
-  int k = t / (2 * d_in);
-  if (k >= n_freqs) return 0.f;
-  int rem = t - k * 2 * d_in;
-  int fn = rem / d_in, dim = rem - fn * d_in;
+// Positional-encoding columns come from a per-CTA table (one entry per column, built once): the column -> (frequency,
+// sin / cos, input dimension) mapping needs two integer divisions by run-time values, ~600 cycles per element when done
+// inline (tools/chain_trace.py: 20 k cycles of the reverse sweep's gradient step, 10 k of the tangent's prologue).
+struct PeEntry {
+  float mult;
+  int32_t code;   // dim | kind << 4 ; kind: 0 zero, 1 identity, 2 sin, 3 cos
+};
+__device__ __forceinline__ PeEntry pe_entry(int c, int d_in, int n_freqs) {
+  PeEntry e{0.f, 0};
+  if (c < d_in) {
+    e.mult = 1.f;
+    e.code = c | (1 << 4);
+  } else if (c < d_in * (1 + 2 * n_freqs)) {
+    const int t = c - d_in, k = t / (2 * d_in), rem = t - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
+    e.mult = (float)(1 << k);
+    e.code = dim | ((fn ? 3 : 2) << 4);
+  }
+  return e;
+}
+__device__ __forceinline__ float pe_eval(const float (&xv)[4], PeEntry e) {
+  const int dim = e.code & 15, kind = e.code >> 4;
+  const float xs = dim == 0 ? xv[0] : (dim == 1 ? xv[1] : (dim == 2 ? xv[2] : xv[3]));
   // MUFU sin/cos: |arg| <= 2^(n_freqs-1) * |x| ~ 1e2 -> abs. error ~1e-5, far below the fp16 operand rounding (5e-4)
-  float arg = xv[dim] * (float)(1 << k);
-  return fn ? __cosf(arg) : __sinf(arg);
+  const float arg = xs * e.mult;
+  return kind == 1 ? xs : (kind == 2 ? __sinf(arg) : (kind == 3 ? __cosf(arg) : 0.f));
 }
 // d PE_c / d x_dim(c)
-__device__ __forceinline__ float pe_dcol(const float (&xv)[4], int d_in, int n_freqs, int c, int* dim_out) {
-  if (c < d_in) { *dim_out = c; return 1.f; }
-  int t = c - d_in;
-  int k = t / (2 * d_in);
-  if (k >= n_freqs) { *dim_out = 0; return 0.f; }
-  int rem = t - k * 2 * d_in;
-  int fn = rem / d_in, dim = rem - fn * d_in;
-  float f = (float)(1 << k);
-  float arg = xv[dim] * f;
+__device__ __forceinline__ float pe_deval(const float (&xv)[4], PeEntry e, int* dim_out) {
+  const int dim = e.code & 15, kind = e.code >> 4;
+  const float xs = dim == 0 ? xv[0] : (dim == 1 ? xv[1] : (dim == 2 ? xv[2] : xv[3]));
+  const float arg = xs * e.mult;
   *dim_out = dim;
-  return fn ? (-f * __sinf(arg)) : (f * __cosf(arg));
+  return kind == 1 ? 1.f : (kind == 2 ? e.mult * __cosf(arg) : (kind == 3 ? -e.mult * __sinf(arg) : 0.f));
 }
+constexpr int kPeTabCols = 128;   // widest positional encoding the chain kernels index (table lives at kOffVec)
 
 __device__ __forceinline__ float clamp_w(float y0, float sphere) { return (y0 < sphere) ? 1.f : ((y0 == sphere) ? 0.5f : 0.f); }
 
@@ -554,6 +564,8 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
     static_assert(!kHasBias || (EPI & (epi_bit(EP_REVERSE) | epi_bit(EP_PEGRAD))) == 0, "bias table shares the stash region");
     static_assert(kMaxSteps * 256 * 4 <= kTile * kStashLd * 4, "bias table must fit the stash region");
     float* btab = stash;
+    PeEntry* petab = reinterpret_cast<PeEntry*>(smem + kOffVec);   // visible after the first tile's named barrier
+    if (et < kPeTabCols) petab[et] = pe_entry(et, ch.d_in, ch.n_freqs);
     if (kHasBias) {
       for (int s = 0; s < ch.n_steps; ++s) {
         const float* b = ch.st[s].bias;
@@ -715,7 +727,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
         const int c0 = pc * 16;
         if (PRO == PRO_PE) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_col(xv, ch.d_in, ch.n_freqs, c0 + i) : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < pe_w) ? pe_eval(xv, petab[c0 + i]) : 0.f;
         } else if (PRO == PRO_LOAD_ULAST) {
           ld_row16(sA + b * kBlk, m, cq, v);
 #pragma unroll
@@ -745,7 +757,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
               float r = 0.f;
               if (live && c < n_small) {
                 if (c < o_view) r = ch.points[p * 3 + c];
-                else if (c < o_n) r = pe_col(vv, 3, ch.view_freqs, c - o_view);
+                else if (c < o_n) r = pe_eval(vv, pe_entry(c - o_view, 3, ch.view_freqs));
                 else r = ch.normals[p * 3 + (c - o_n)];
               }
               v[i] = r;
@@ -769,7 +781,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             float r = 0.f;
             if (live && c < pe_w) {
               int dim;
-              float j = pe_dcol(xv, ch.d_in, ch.n_freqs, c, &dim);
+              float j = pe_deval(xv, petab[c], &dim);
               r = j * dg[dim];
             }
             v[i] = r;
@@ -879,7 +891,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
                 const int n = col0 + i;
                 float r = 0.f;
                 if (n < st.n_valid) r = softplus100_fast(acc[i] + btab_s[n & 255], c_lo, c_hi);
-                else if (st.flags & TC_PEFILL) r = pe_col(xv, ch.d_in, ch.n_freqs, n - st.n_valid) * st.scale;
+                else if (st.flags & TC_PEFILL) r = pe_eval(xv, petab[n - st.n_valid]) * st.scale;
                 o[i] = r;
               }
             }
@@ -1004,7 +1016,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
                 const int n = col0 + i;
                 if (n >= st.n_valid && n - st.n_valid < pe_w) {
                   int dim;
-                  float j = pe_dcol(xv, ch.d_in, ch.n_freqs, n - st.n_valid, &dim);
+                  float j = pe_deval(xv, petab[n - st.n_valid], &dim);
                   o[i] = live ? j * dg[dim] * st.scale : 0.f;
                 }
               }
@@ -1066,7 +1078,7 @@ __global__ void __launch_bounds__(kCtrlThreads + NW * 32, 1) tc_chain_kernel(con
             float g[4] = {0.f, 0.f, 0.f, 0.f};
             for (int c = 0; c < pe_w; ++c) {
               int dim;
-              float j = pe_dcol(xv, ch.d_in, ch.n_freqs, c, &dim);
+              float j = pe_deval(xv, petab[c], &dim);
               g[dim] += j * stash[m * kStashLd + c];
             }
             float y0 = ch.yin[p * ch.ldy];

@@ -49,18 +49,6 @@ struct F2Bars {
 };
 static_assert(sizeof(F2Bars) <= 256, "barrier block overflows its reservation");
 
-struct PeEntry {
-  float mult;
-  int32_t code;   // dim | kind << 4 ; kind: 0 zero, 1 identity, 2 sin, 3 cos
-};
-
-__device__ __forceinline__ float pe_eval(const float (&xv)[4], PeEntry e) {
-  const int dim = e.code & 15, kind = e.code >> 4;
-  const float xs = dim == 0 ? xv[0] : (dim == 1 ? xv[1] : (dim == 2 ? xv[2] : xv[3]));
-  const float arg = xs * e.mult;
-  return kind == 1 ? xs : (kind == 2 ? __sinf(arg) : (kind == 3 ? __cosf(arg) : 0.f));
-}
-
 // log2(1 + u) = u q(u), u in [0, 1]; minimax fit (max abs error 1.03e-4)
 constexpr float kL2pC1 = 1.4390146732330322f, kL2pC2 = -0.6799439787864685f, kL2pC3 = 0.32559555768966675f,
                 kL2pC4 = -0.08476857841014862f;
@@ -223,17 +211,8 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
         if (et < 256) btab[s * 256 + et] = (b && et < nv) ? b[et] * mul : 0.f;
       }
       if (et < kF2PeCols) {
-        PeEntry e{0.f, 0};
-        const int c = et, d_in = ch.d_in;
-        if (c < d_in) {
-          e.mult = 1.f;
-          e.code = c | (1 << 4);
-        } else if (c < pe_w) {
-          const int t = c - d_in, k = t / (2 * d_in), rem = t - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
-          e.mult = (float)(1 << k);
-          e.code = dim | ((fn ? 3 : 2) << 4);
-        }
-        petab[c] = e;
+        const int c = et;
+        petab[c] = pe_entry(c, ch.d_in, ch.n_freqs);
       }
       named_bar_sync(1, kF2NW * 32);
     }
@@ -322,7 +301,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) tc_fwd2_kernel(const __grid_con
               float rv = 0.f;
               if (live[T] && c < n_small) {
                 if (c < o_view) rv = ch.points[pt[T] * 3 + c];
-                else if (c < o_n) rv = pe_col(vv, 3, ch.view_freqs, c - o_view);
+                else if (c < o_n) rv = pe_eval(vv, pe_entry(c - o_view, 3, ch.view_freqs));
                 else rv = ch.normals[pt[T] * 3 + (c - o_n)];
               }
               v[i] = rv;

@@ -315,17 +315,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     const uint32_t tm_row = tmem + ((uint32_t)(q * 32) << 16);
     if constexpr (MODE == kF2Sdf) {
       if (et < kF2PeCols) {
-        PeEntry e{0.f, 0};
-        const int c = et, d_in = ch.d_in;
-        if (c < d_in) {
-          e.mult = 1.f;
-          e.code = c | (1 << 4);
-        } else if (c < pe_w) {
-          const int tt = c - d_in, k = tt / (2 * d_in), rem = tt - k * 2 * d_in, fn = rem / d_in, dim = rem - fn * d_in;
-          e.mult = (float)(1 << k);
-          e.code = dim | ((fn ? 3 : 2) << 4);
-        }
-        petab[c] = e;
+        const int c = et;
+        petab[c] = pe_entry(c, ch.d_in, ch.n_freqs);
       }
       named_bar_sync(1, kF3NW * 32);
     }
