@@ -30,15 +30,21 @@ namespace tc {
 #endif
 constexpr int kF3NW = 16;
 constexpr int kF3Threads = kCtrlThreads + kF3NW * 32;
-constexpr int kF3MaxSlots = 3;
-template <int MODE>
+constexpr int kF3MaxSlots = 6;
+// PAIR: two CTAs of a cluster work as one cta_group::2 unit.  Every CTA keeps its own 128-point tile (A_hi, A_lo, its
+// TMEM accumulators) and streams only HALF of every weight block (128 of the 256 output rows); one tcgen05.mma with
+// M = 256 multiplies both tiles by the whole block.  The kernel is bound by shared-memory bandwidth (per layer and tile:
+// 48 instructions x 12 KB of operands + 384 KB of weight fills + 128 KB of activation stores against 128 B/clk), and the
+// pair halves the weight side of it: 8 KB of operands per instruction and CTA, 192 KB of fills.
+template <int MODE, bool PAIR>
 struct F3Cfg {
   static constexpr int kMaxKB = MODE == kF2Render ? 5 : 4;
-  static constexpr int kSlots = MODE == kF2Render ? 2 : 3;
+  static constexpr int kSlotBytes = PAIR ? kWSlot / 2 : kWSlot;
+  static constexpr int kSlots = (MODE == kF2Render ? 2 : 3) * (PAIR ? 2 : 1);
   static constexpr int kOffAhi = 0;
   static constexpr int kOffAlo = kMaxKB * kBlk;
   static constexpr int kOffW = 2 * kMaxKB * kBlk;
-  static constexpr int kOffPe = kOffW + kSlots * kWSlot;
+  static constexpr int kOffPe = kOffW + kSlots * kSlotBytes;
   static constexpr int kPeBytes = MODE == kF2Render ? 0 : kF2PeCols * 8;
   static constexpr int kOffBar = kOffPe + kPeBytes;
   static constexpr int kSmemBytes = kOffBar + 512;
@@ -46,14 +52,79 @@ struct F3Cfg {
 };
 
 struct F3Bars {
-  uint64_t w_full[kF3MaxSlots], w_empty[kF3MaxSlots], a_ready[kMaxKB], s_free[kMaxKB], acc_full;
+  // w_peer (PAIR, leader CTA only): the peer CTA's half of the slot has landed
+  uint64_t w_full[kF3MaxSlots], w_empty[kF3MaxSlots], w_peer[kF3MaxSlots], a_ready[kMaxKB], s_free[kMaxKB], acc_full;
   uint32_t tmem;
 };
 static_assert(sizeof(F3Bars) <= 512, "barrier block overflows its reservation");
 
+// ---- cta_group::2 building blocks (cluster of two CTAs) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (CTA-scope release)
+// semantics: the data the arrival publishes stays in the arriving CTA's shared memory, where fence.proxy.async has made it
+// visible to the tensor core; an explicit .release.cluster costs ~900 cycles per arrival (the peer's epilogue fell 3.7 k
+// cycles per layer behind the leader's: tools/f3_trace.py)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+// wait that also acquires the writes released by arrivals from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE_%=;\n\t"
+      "bra WAITC_LOOP_%=;\n\t"
+      "WAITC_DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far arrives on `bar` in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 // hi / lo halves of 16 consecutive columns of row m
+template <bool PAIR>
 __device__ __forceinline__ void f3_umma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
-  if (!(SVS_F3_EXP & 1)) umma_f16(d, a, b, idesc, accum);
+  if (SVS_F3_EXP & 1) return;
+  if constexpr (PAIR) umma_f16_2cta(d, a, b, idesc, accum);
+  else umma_f16(d, a, b, idesc, accum);
 }
 __device__ __forceinline__ void st_row16_split(uint8_t* blk_hi, uint8_t* blk_lo, int m, int cq, const float (&v)[16]) {
 #pragma unroll
@@ -119,7 +190,7 @@ __device__ __forceinline__ float pe_eval_precise(const float (&xv)[4], PeEntry e
 static bool fwd3_supports(const TcChain& ch) {
   const bool render = ch.prologue == PRO_RENDER_IN;
   if (ch.prologue != PRO_PE && !render) return false;
-  const int max_kb = render ? F3Cfg<kF2Render>::kMaxKB : F3Cfg<kF2Sdf>::kMaxKB;
+  const int max_kb = render ? F3Cfg<kF2Render, false>::kMaxKB : F3Cfg<kF2Sdf, false>::kMaxKB;
   if (ch.pro_kb > max_kb || ch.pro_colsum >= 0 || ch.n_steps < 1) return false;
   if (!render && (ch.d_in > 4 || ch.d_in * (1 + 2 * ch.n_freqs) > kF2PeCols)) return false;
   if (render && ((ch.F & 63) != 0 || ch.F > 256 || ch.pro_kb != ch.F / 64 + 1)) return false;
@@ -138,9 +209,9 @@ static bool fwd3_supports(const TcChain& ch) {
   return ch.st[0].KB == ch.pro_kb;
 }
 
-template <int MODE>
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_constant__ TcChain ch) {
-  typedef F3Cfg<MODE> Cfg;
+  typedef F3Cfg<MODE, PAIR> Cfg;
   constexpr int NS = Cfg::kSlots;
   constexpr int NCG = kF3NW / 4;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -151,26 +222,36 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
   F3Bars* bars = reinterpret_cast<F3Bars*>(smem + Cfg::kOffBar);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PAIR: CTA `rank` of the cluster takes tile 2 i + rank of tile pair i (an odd tile count leaves the last pair's second
+  // CTA a tile behind the end: it runs the barrier protocol on zeros and neither reads nor writes global memory)
+  uint32_t rank = 0;
+  if constexpr (PAIR) rank = cluster_ctarank();
+#define F3_TILES(t) int t = (PAIR ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x); t < (PAIR ? 2 * ((ch.n_tiles + 1) >> 1) : ch.n_tiles); t += (int)gridDim.x
   // chains that save nothing (sampler sdf, eval forward): no store lane, no hand-back of the blocks
   bool any_save = ch.pro_save >= 0;
   for (int s = 0; s < ch.n_steps; ++s) any_save |= ch.st[s].save >= 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->a_ready[i], kF3NW);   // one per 64-column block: every epilogue warp writes one 16-column piece of it
+    for (int i = 0; i < NS; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); mbar_init(&bars->w_peer[i], 1); }
+    // one per 64-column block: every epilogue warp writes one 16-column piece of it; the pair's leader also counts the peer's
+    for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->a_ready[i], (PAIR && rank == 0) ? 2 * kF3NW : kF3NW);
     for (int i = 0; i < kMaxKB; ++i) mbar_init(&bars->s_free[i], 1);
     mbar_init(&bars->acc_full, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc(&bars->tmem, 512);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_2cta(&bars->tmem, 512);
+    else tmem_alloc(&bars->tmem, 512);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem = bars->tmem;
 
   if (warp == 0) {
     // ===== weight producer: per step the cross-term blocks (W_lo(kb), W_hi(kb) for every kb), then the W_hi blocks again
-    //       for the main term (see the MMA issuer for why the main term goes last) =====
+    //       for the main term (see the MMA issuer for why the main term goes last).  PAIR: this CTA's half of the rows. =====
     if (lane == 0) {
       uint32_t seq = 0;
       auto load = [&](const uint8_t* src, uint32_t bytes) {
@@ -180,18 +261,20 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         mbar_wait(&bars->w_empty[slot], (use & 1) ^ 1);
         if (SVS_F3_EXP & 8) { mbar_arrive(&bars->w_full[slot]); return; }
         mbar_arrive_expect_tx(&bars->w_full[slot], bytes);
-        bulk_g2s(sW + slot * kWSlot, src, bytes, &bars->w_full[slot]);
+        bulk_g2s(sW + slot * Cfg::kSlotBytes, src, bytes, &bars->w_full[slot]);
       };
-      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+      for (F3_TILES(t)) {
         for (int s = 0; s < ch.n_steps; ++s) {
           const TcStep& st = ch.st[s];
-          const uint32_t bytes = (uint32_t)st.n_pad * 128u;
+          const uint32_t blk = (uint32_t)st.n_pad * 128u;                 // one 64-column block of the image
+          const uint32_t bytes = PAIR ? blk / 2 : blk;                      // rows [rank n_pad / 2, +n_pad / 2) of it
+          const size_t off = PAIR ? (size_t)rank * bytes : 0;
           for (int kb = 0; kb < st.KB; ++kb) {
-            load(st.w_lo + (size_t)kb * bytes, bytes);
-            load(st.w + (size_t)kb * bytes, bytes);
+            load(st.w_lo + (size_t)kb * blk + off, bytes);
+            load(st.w + (size_t)kb * blk + off, bytes);
           }
           // main term, last block first: W_hi(KB-1) is still in its slot from the cross term
-          for (int kb = st.KB - 2; kb >= 0; --kb) load(st.w + (size_t)kb * bytes, bytes);
+          for (int kb = st.KB - 2; kb >= 0; --kb) load(st.w + (size_t)kb * blk + off, bytes);
         }
       }
     }
@@ -203,16 +286,48 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     //       2^-35 of the result), and only the 4 KB main-term instructions see the full magnitude: 16 truncations per
     //       layer instead of 48 (measured sdf error 2.4e-5 -> see DESIGN.md).  Cross-term k-steps trail the epilogue of
     //       the previous step at 16-column granularity. =====
-    if (lane == 0) {
+    if (PAIR && rank != 0) {
+      // the peer has no MMAs to issue (the leader's instructions drive both tensor cores): its lane relays "my half of the
+      // slot has landed" to the leader
+      if (lane == 0) {
+        uint32_t seq = 0;
+        for (F3_TILES(t)) {
+          for (int s = 0; s < ch.n_steps; ++s) {
+            const int n_items = 3 * ch.st[s].KB - 1;
+            for (int i = 0; i < n_items; ++i) {
+              const int slot = seq % NS;
+              const uint32_t use = seq / NS;
+              ++seq;
+              mbar_wait(&bars->w_full[slot], use & 1);
+              mbar_arrive_cluster(&bars->w_peer[slot], 0);
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t seq = 0, n_step = 0, a_par = 0;
 #ifdef SVS_F3_TRACE
       const int trace_lane = 0;
       uint32_t trace_n = 0;
 #endif
-      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+      // waits for the weight slot (PAIR: both halves) ; operand blocks published by the epilogue (PAIR: of both CTAs)
+      auto wait_w = [&](int slot, uint32_t use) {
+        mbar_wait(&bars->w_full[slot], use & 1);
+        if constexpr (PAIR) mbar_wait_cluster(&bars->w_peer[slot], use & 1);
+      };
+      auto wait_a = [&](int kb) {
+        if constexpr (PAIR) mbar_wait_cluster(&bars->a_ready[kb], (a_par >> kb) & 1);
+        else mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+        a_par ^= 1u << kb;
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) umma_commit_2cta(bar);
+        else umma_commit(bar);
+      };
+      for (F3_TILES(t)) {
         for (int s = 0; s < ch.n_steps; ++s, ++n_step) {
           const TcStep& st = ch.st[s];
-          const uint32_t idesc = make_idesc_f16(kTile, st.n_pad, 0, 0);
+          const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTile : kTile, st.n_pad, 0, 0);
           const uint32_t acc = tmem + (n_step & 1) * 256;
           const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x;
           F3_EV(tr, 1, s, 0);
@@ -222,51 +337,50 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               const int slot = seq % NS;
               const uint32_t use = seq / NS;
               ++seq;
-              mbar_wait(&bars->w_full[slot], use & 1);
+              wait_w(slot, use);
               F3_EV(tr, 2, s, kb);
-              mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
+              wait_a(kb);
               F3_EV(tr, 3, s, kb);
-              a_par ^= 1u << kb;
               tc_fence_after();
-              const uint32_t b0 = smem_u32(sW + slot * kWSlot);
+              const uint32_t b0 = smem_u32(sW + slot * Cfg::kSlotBytes);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
-              umma_commit(&bars->w_empty[slot]);
+                f3_umma<PAIR>(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, (kb | j) != 0);
+              commit(&bars->w_empty[slot]);
             }
             {   // A_lo(kb) x W_hi(kb); the last block stays for the first main-term block
               const int slot = seq % NS;
               const uint32_t use = seq / NS;
               ++seq;
-              mbar_wait(&bars->w_full[slot], use & 1);
+              wait_w(slot, use);
               F3_EV(tr, 4, s, kb);
               tc_fence_after();
-              const uint32_t b0 = smem_u32(sW + slot * kWSlot);
+              const uint32_t b0 = smem_u32(sW + slot * Cfg::kSlotBytes);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                f3_umma(acc, make_smem_desc(al + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+                f3_umma<PAIR>(acc, make_smem_desc(al + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
               if (kb == st.KB - 1) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+                  f3_umma<PAIR>(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
               }
-              umma_commit(&bars->w_empty[slot]);
+              commit(&bars->w_empty[slot]);
             }
           }
           for (int kb = st.KB - 2; kb >= 0; --kb) {   // main term A_hi(kb) x W_hi(kb), remaining blocks
             const int slot = seq % NS;
             const uint32_t use = seq / NS;
             ++seq;
-            mbar_wait(&bars->w_full[slot], use & 1);
+            wait_w(slot, use);
             F3_EV(tr, 5, s, kb);
             tc_fence_after();
-            const uint32_t ah = smem_u32(sAhi + kb * kBlk), b0 = smem_u32(sW + slot * kWSlot);
+            const uint32_t ah = smem_u32(sAhi + kb * kBlk), b0 = smem_u32(sW + slot * Cfg::kSlotBytes);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              f3_umma(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
-            umma_commit(&bars->w_empty[slot]);
+              f3_umma<PAIR>(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+            commit(&bars->w_empty[slot]);
           }
-          umma_commit(&bars->acc_full);
+          commit(&bars->acc_full);
           F3_EV(tr, 6, s, 0);
         }
       }
@@ -279,9 +393,10 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         mbar_wait(&bars->a_ready[kb], (a_par >> kb) & 1);
         a_par ^= 1u << kb;
       };
-      for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+      for (F3_TILES(t)) {
+        const bool real = t < ch.n_tiles;   // the pair's padding tile saves nothing
         for (int b = 0; b < ch.pro_kb; ++b) consume(b);
-        if (ch.pro_save >= 0) {
+        if (ch.pro_save >= 0 && real) {
           bulk_s2g(ch.img[ch.pro_save].base + (size_t)t * ch.img[ch.pro_save].tile_bytes, sAhi, (uint32_t)ch.pro_kb * kBlk);
           bulk_commit();
           bulk_wait_read<0>();
@@ -292,12 +407,12 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           if (st.next_kb > 0) {
             for (int c = 0; c < st.next_kb; ++c) {
               consume(c);
-              if (st.save >= 0) {
+              if (st.save >= 0 && real) {
                 bulk_s2g(ch.img[st.save].base + (size_t)t * ch.img[st.save].tile_bytes + (size_t)c * kBlk, sAhi + c * kBlk, kBlk);
                 bulk_commit();
               }
             }
-            if (st.save >= 0) bulk_wait_read<0>();
+            if (st.save >= 0 && real) bulk_wait_read<0>();
             for (int c = 0; c < st.next_kb; ++c) mbar_arrive(&bars->s_free[c]);
           } else if (s + 1 < ch.n_steps) {
             for (int c = 0; c < ch.st[s + 1].KB; ++c) consume(c);
@@ -326,7 +441,15 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
     uint32_t trace_n = 0;
 #endif
 
-    for (int t = blockIdx.x; t < ch.n_tiles; t += gridDim.x) {
+    // a block of A is published to the MMA issuer (PAIR: the leader's, which also counts this CTA's warps when it is the
+    // peer) and to this CTA's store lane
+    auto publish = [&](int kb) {
+      mbar_arrive(&bars->a_ready[kb]);
+      if constexpr (PAIR) {
+        if (rank != 0) mbar_arrive_cluster(&bars->a_ready[kb], 0);
+      }
+    };
+    for (F3_TILES(t)) {
       const int64_t p = (int64_t)t * kTile + m;
       const bool live = p < ch.P;
       float xv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -346,7 +469,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           st_row16_split(sAhi + b * kBlk, sAlo + b * kBlk, m, pc & 3, v);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->a_ready[b]);
+          if (lane == 0) publish(b);
         }
       } else {
         // A = [feat (F columns) | points(3) if idr, PE(view), normals(3) if idr].  Features are fp32 row-major: warp ew
@@ -406,7 +529,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         fence_proxy_async();
         named_bar_sync(1, kF3NW * 32);
         if (lane == 0)
-          for (int b = 0; b < ch.pro_kb; ++b) mbar_arrive(&bars->a_ready[b]);
+          for (int b = 0; b < ch.pro_kb; ++b) publish(b);
       }
       for (int b = 0; b < ch.pro_kb; ++b) fgen ^= 1u << b;
 
@@ -433,7 +556,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)
           if (lane == 0)
-            for (int b = 0; b < ch.st[s + 1].KB; ++b) mbar_arrive(&bars->a_ready[b]);
+            for (int b = 0; b < ch.st[s + 1].KB; ++b) publish(b);
         }
         if constexpr (MODE == kF2Sdf) {
           if (st.epi == EP_SOFTPLUS && st.n_valid == 256 && st.next_kb == 4) {
@@ -458,7 +581,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
               F3_EV(tr, 11, s, ew * 4 + k);
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&bars->a_ready[k]);
+              if (lane == 0) publish(k);
               F3_EV(tr, 12, s, ew * 4 + k);
             }
             fgen ^= 15u;
@@ -575,7 +698,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->a_ready[c]);
+            if (lane == 0) publish(c);
           }
         }
         if (writes_a)
@@ -588,21 +711,54 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem, 512);
+  if constexpr (PAIR) cluster_sync_all();   // no CTA leaves (or frees its TMEM) while the peer may still arrive on its barriers
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_dealloc_2cta(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
+#undef F3_TILES
+
 template <int MODE>
-static int launch_fwd3_t(const TcChain& ch, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<MODE>::kSmemBytes));
-    attr_set = true;
+static int launch_fwd3_t(const TcChain& ch, int grid, int n_sms, cudaStream_t st) {
+  // cta_group::2 pairs (clusters of two CTAs, one tile each): opt-in with SVS_F3_PAIR=1.  Measured on B200 (131 072 points,
+  // tools/f3_exp.py): 0.438 ms against 0.413 ms for independent CTAs — the chain's critical path per layer is epilogue
+  // (~6 k cycles) + the 24 main-term instructions that must follow it (3.1 k, tensor-bound) + hand-offs, none of which the
+  // halved weight traffic shortens, and the pair runs at the pace of its slower CTA (tools/f3_trace.py).
+  static const bool pair = getenv("SVS_F3_PAIR") != nullptr && getenv("SVS_F3_PAIR")[0] == '1';
+  if (pair && ch.n_tiles >= 2 && n_sms >= 2) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd3_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<MODE, true>::kSmemBytes));
+      attr_set = true;
+    }
+    const int tile_pairs = (ch.n_tiles + 1) / 2, cta_pairs = n_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (tile_pairs < cta_pairs ? tile_pairs : cta_pairs));
+    cfg.blockDim = dim3(kF3Threads);
+    cfg.dynamicSmemBytes = F3Cfg<MODE, true>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SVS_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_fwd3_kernel<MODE, true>, ch));
+    return SVS_OK;
   }
-  tc_fwd3_kernel<MODE><<<grid, kF3Threads, F3Cfg<MODE>::kSmemBytes, st>>>(ch);
+  static bool attr_set1 = false;
+  if (!attr_set1) {
+    SVS_CUDA_OK(cudaFuncSetAttribute(tc_fwd3_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<MODE, false>::kSmemBytes));
+    attr_set1 = true;
+  }
+  tc_fwd3_kernel<MODE, false><<<grid, kF3Threads, F3Cfg<MODE, false>::kSmemBytes, st>>>(ch);
   return SVS_OK;
 }
-static int launch_fwd3(const TcChain& ch, int grid, cudaStream_t st) {
-  return ch.prologue == PRO_RENDER_IN ? launch_fwd3_t<kF2Render>(ch, grid, st) : launch_fwd3_t<kF2Sdf>(ch, grid, st);
+static int launch_fwd3(const TcChain& ch, int grid, int n_sms, cudaStream_t st) {
+  return ch.prologue == PRO_RENDER_IN ? launch_fwd3_t<kF2Render>(ch, grid, n_sms, st) : launch_fwd3_t<kF2Sdf>(ch, grid, n_sms, st);
 }
 
 }  // namespace tc

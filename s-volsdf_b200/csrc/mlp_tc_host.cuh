@@ -371,7 +371,7 @@ static int launch_chain(TcChain& ch, const char* name, double flops, double byte
   ProfScope ps(name, flops, bytes, st);
   if (ch.split) {
     if (!fwd3_supports(ch)) { set_error("launch_chain: chain not supported by the split-operand forward kernel"); return SVS_ERR_UNSUPPORTED; }
-    SVS_TRY(launch_fwd3(ch, grid, st));
+    SVS_TRY(launch_fwd3(ch, grid, num_sms(), st));
     SVS_LAUNCH_OK();
     return SVS_OK;
   }
