@@ -26,7 +26,7 @@ namespace svs {
 namespace tc {
 
 #ifndef SVS_F3_EXP
-#define SVS_F3_EXP 0   // measurement builds only (tools/f3_exp.sh): 1 no MMA, 2 no MUFU, 4 no A stores, 8 no weight copies, 16 idle epilogue
+#define SVS_F3_EXP 0   // measurement builds only (tools/f3_exp.sh): 1 no MMA, 2 no MUFU, 4 no A stores, 8 no weight copies, 16 idle epilogue, 32 main term of the last block only
 #endif
 constexpr int kF3NW = 16;
 constexpr int kF3Threads = kCtrlThreads + kF3NW * 32;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
           const TcStep& st = ch.st[s];
           const uint32_t idesc = make_idesc_f16(PAIR ? 2 * kTile : kTile, st.n_pad, 0, 0);
           const uint32_t acc = tmem + (n_step & 1) * 256;
-          const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x;
+          [[maybe_unused]] const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x;
           F3_EV(tr, 1, s, 0);
           for (int kb = 0; kb < st.KB; ++kb) {
             const uint32_t ah = smem_u32(sAhi + kb * kBlk), al = smem_u32(sAlo + kb * kBlk);
@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
             const uint32_t ah = smem_u32(sAhi + kb * kBlk), b0 = smem_u32(sW + slot * Cfg::kSlotBytes);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              f3_umma<PAIR>(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
+              if (!(SVS_F3_EXP & 32))   // measurement: what a tail half as long would buy
+                f3_umma<PAIR>(acc, make_smem_desc(ah + j * 32, 0, 1024), make_smem_desc(b0 + j * 32, 0, 1024), idesc, 1);
             commit(&bars->w_empty[slot]);
           }
           commit(&bars->acc_full);
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(kF3Threads, 1) tc_fwd3_kernel(const __grid_con
         mbar_wait_relaxed(&bars->acc_full, n_acc & 1);
         ++n_acc;
         tc_fence_after();
-        const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 15 || ew == 5);
+        [[maybe_unused]] const bool tr = blockIdx.x == 0 && t == 2 * (int)gridDim.x && lane == 0 && (ew == 0 || ew == 15 || ew == 5);
         F3_EV(tr, 7, s, ew);
         if (!writes_a && has_next) {
           // A is not rewritten by this step: the next step's MMAs may start at once (into the other accumulator)

@@ -186,3 +186,47 @@ def test_grouped_render_equals_the_reference_chunk_loop(engine):
     assert len(set(iters)) > 1, iters          # the groups really stop at different iterations
     for k in ('rgb_values', 'depth_values', 'normal_map'):
         assert torch.equal(got[k], torch.cat([p[k] for p in parts], 0)), k
+
+
+def test_cta_pair_mode_matches_single_cta_mode(tmp_path):
+    """SVS_F3_PAIR=1 (cta_group::2: clusters of two CTAs, one M = 256 instruction per weight block for both tiles) computes
+    the same arithmetic in the same order as independent CTAs: sdf / y bit-identical, including an odd tile count (the
+    pair's padding tile); saved activations: the gradients of a small step agree to the rounding order of the atomics.  The switch is read once
+    per process, so each mode runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch, warnings
+warnings.filterwarnings('ignore')
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from helpers import build_model
+import svolsdf_b200._lib as L
+m = build_model('dtu', perturb=True, beta=0.05, device='cuda').set_engine(L.ENGINE_TC_SPLIT).train()
+g = torch.Generator().manual_seed(5)
+out = {}
+for P in (129, 5000, 12345):          # 2, 40, 97 tiles (odd: padding tile in the last pair)
+    x = ((torch.rand(P, 3, generator=g) * 2 - 1) * 1.2).cuda()
+    with torch.no_grad():
+        out['s%%d' %% P] = m.implicit_network.get_sdf_vals(x).cpu()
+        out['y%%d' %% P] = m.implicit_network(x).cpu()
+x = ((torch.rand(3000, 3, generator=g) * 2 - 1) * 1.2).cuda()
+sdf, feat, grad = m.implicit_network.get_outputs(x)
+(sdf.sum() + feat.square().mean() + grad.square().sum()).backward()
+for n, p in m.implicit_network.named_parameters():
+    out['g_' + n] = p.grad.cpu()
+torch.save(out, sys.argv[1])
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ('0', '1'):
+        env = dict(os.environ, SVS_F3_PAIR=mode)
+        path = str(tmp_path / ('out%s.pt' % mode))
+        subprocess.run([sys.executable, '-c', script, path], check=True, env=env, timeout=300)
+        res[mode] = torch.load(path)
+    assert res['0'].keys() == res['1'].keys()
+    # forward results bit for bit; weight gradients are sums of fp32 atomics (run-to-run rounding order) over identical tiles
+    bad = {k: float((res['0'][k] - res['1'][k]).abs().max()) for k in res['0'] if not k.startswith('g_') and not torch.equal(res['0'][k], res['1'][k])}
+    assert not bad, bad
+    for k in res['0']:
+        if k.startswith('g_'):
+            assert rel_err(res['1'][k], res['0'][k]) < 1e-4, (k, rel_err(res['1'][k], res['0'][k]))
