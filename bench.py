@@ -78,11 +78,14 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launches nvidia-smi (10 ms period).  Call it BEFORE the warm-up: the tool needs ~0.1 s to deliver its first
+        line, longer than a 20-step timed region; mark()/stop() then keep the samples that fall inside the region."""
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '20'],
+                                          '--format=csv,noheader,nounits', '-lms', '10'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -91,7 +94,14 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """Call at the start and at the end of the timed region."""
+        if self.t0 is None:
+            self.t0 = time.monotonic()
+        else:
+            self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -101,9 +111,18 @@ class ClockSampler(object):
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        window = 'timed region'
+        t0, t1 = self.t0, self.t1 if self.t1 is not None else time.monotonic()
+        lines = [ln for ts, ln in self.lines if t0 is None or t0 <= ts <= t1 + 0.015]
+        if not lines and t0 is not None:
+            # a region shorter than the sampling period: the samples taken under the same load right after it (the
+            # end-to-end region replays the same step) stand in
+            lines = [ln for ts, ln in self.lines if ts >= t0]
+            window = 'timed + end-to-end regions'
+        self.lines = [(0.0, ln) for ln in lines]
         sm, mx, reasons = [], None, set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        for _ts, ln in self.lines:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 7:
                 continue
@@ -117,7 +136,7 @@ class ClockSampler(object):
                     reasons.add(n)
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -558,6 +577,8 @@ def run_ours(args):
             return float(t.item())
         return ms
 
+    clocks = ClockSampler(local)
+    clocks.start()           # long before the timed region: nvidia-smi needs 0.1 s (1 GPU) .. 1 s (8 GPUs) to deliver its first sample
     rig = TrainRig(args, R, engine, world, rank, dev, W + max(K, n_prof), args.scene)
     Rg = rig.Rg
     step_mode = rig.step_mode
@@ -566,11 +587,10 @@ def run_ours(args):
     # ---- device-timed region: inputs resident in HBM ----
     for i in range(W):
         rig.step_device(i)
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
+    clocks.mark()
     ms_step = timed(lambda i: rig.step_device(W + i), K, barrier, max_over_ranks)
-    clk = clocks.stop()
+    clocks.mark()
     launches = rig.launches_per_step * K
     value = Rg / (ms_step * 1e-3)
 
@@ -584,6 +604,7 @@ def run_ours(args):
         _, nb = rig.step_e2e()
         h2d[0] = nb
     ms_e2e = timed(e2e_step, K, barrier, max_over_ranks)
+    clk = clocks.stop()      # samples inside the device-timed region (or, if it was shorter than a sampling period, up to here)
     h2d_bytes = h2d[0] + sum(v.numel() * v.element_size() for v in rig.inp_pin.values()) + rig.gt_pin.numel() * 4
 
     # ---- per-kernel profile pass (CUDA events around every launch of the library; not part of the timing) ----
