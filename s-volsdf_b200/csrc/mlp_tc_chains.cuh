@@ -223,7 +223,8 @@ static int sdf_outputs_backward(const svs_mlp_desc* d, const Layout& lo, const f
     ch.d_sdf = d_sdf;
     ch.dy_cols = lo.out[L - 1];
     // fp32 rows staged through the aux ring by bulk copies (needs 16-byte aligned rows of the tile's flat array)
-    ch.dy_bulk = (dy != nullptr && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (int64_t)kTile * lo.ldy < 65536 &&
+    static const bool no_bulk = getenv("SVS_DY_BULK") != nullptr && getenv("SVS_DY_BULK")[0] == '0';   // A/B runs, tests of the register path
+    ch.dy_bulk = (!no_bulk && dy != nullptr && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (int64_t)kTile * lo.ldy < 65536 &&
                   lo.ldy <= 64 * kb_of(lo.out[L - 1])) ? 1 : 0;
     ch.dy_magic = (uint32_t)(0x100000000ull / (uint64_t)lo.ldy) + 1u;
     ch.amax = amax;

@@ -188,7 +188,7 @@ def test_grouped_render_equals_the_reference_chunk_loop(engine):
         assert torch.equal(got[k], torch.cat([p[k] for p in parts], 0)), k
 
 
-def test_cta_pair_mode_matches_single_cta_mode(tmp_path):
+def test_cta_pair_mode_and_dy_register_path_match_the_default(tmp_path):
     """SVS_F3_PAIR=1 (cta_group::2: clusters of two CTAs, one M = 256 instruction per weight block for both tiles) computes
     the same arithmetic in the same order as independent CTAs: sdf / y bit-identical, including an odd tile count (the
     pair's padding tile); saved activations: the gradients of a small step agree to the rounding order of the atomics.  The switch is read once
@@ -218,12 +218,17 @@ for n, p in m.implicit_network.named_parameters():
 torch.save(out, sys.argv[1])
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for mode in ('0', '1'):
-        env = dict(os.environ, SVS_F3_PAIR=mode)
+    for mode, env_add in (('0', {'SVS_F3_PAIR': '0'}), ('1', {'SVS_F3_PAIR': '1'}), ('nobulk', {'SVS_DY_BULK': '0'})):
+        env = dict(os.environ, **env_add)
         path = str(tmp_path / ('out%s.pt' % mode))
         subprocess.run([sys.executable, '-c', script, path], check=True, env=env, timeout=300)
         res[mode] = torch.load(path)
     assert res['0'].keys() == res['1'].keys()
+    # SVS_DY_BULK=0: the backward chain converts dy with register loads instead of staging the rows through the aux ring
+    # (the path taken when dy is not 16-byte aligned): same fp16 operand tile, same gradients
+    for k in res['0']:
+        if k.startswith('g_'):
+            assert rel_err(res['nobulk'][k], res['0'][k]) < 1e-4, (k, rel_err(res['nobulk'][k], res['0'][k]))
     # forward results bit for bit; weight gradients are sums of fp32 atomics (run-to-run rounding order) over identical tiles
     bad = {k: float((res['0'][k] - res['1'][k]).abs().max()) for k in res['0'] if not k.startswith('g_') and not torch.equal(res['0'][k], res['1'][k])}
     assert not bad, bad
