@@ -210,7 +210,7 @@ for P in (129, 5000, 12345):          # 2, 40, 97 tiles (odd: padding tile in th
     with torch.no_grad():
         out['s%%d' %% P] = m.implicit_network.get_sdf_vals(x).cpu()
         out['y%%d' %% P] = m.implicit_network(x).cpu()
-x = ((torch.rand(3000, 3, generator=g) * 2 - 1) * 1.2).cuda()
+x = ((torch.rand(3001, 3, generator=g) * 2 - 1) * 1.2).cuda()   # 57 rows in the last tile: its dy bytes are not a multiple of 16
 sdf, feat, grad = m.implicit_network.get_outputs(x)
 (sdf.sum() + feat.square().mean() + grad.square().sum()).backward()
 for n, p in m.implicit_network.named_parameters():
