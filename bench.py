@@ -534,7 +534,7 @@ def mvs_leg(args, engine, dev, R, K):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
-    return {'workload': 'MVS-supervised DTU train step (paper configuration, SURVEY.md 8f-1): forward + cost lookup in 3 source views '
+    return {'workload': 'MVS-supervised DTU train step (paper configuration, SURVEY.md 8f-1): forward + cost lookup in 3 source views fused with the GCE term (svs_mvs_loss) '
                         '(48x288x384 volumes) + VolSDFLoss (L1 + eikonal + GCE(0.5) on the weights + annealed sparsity) + backward '
                         '+ clip + Adam, one CUDA graph', 'rays': R, 'value': R / (ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': ms,
             'steps': K, 'warmup': 3, 'loss': float(step.loss)}

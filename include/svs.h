@@ -27,7 +27,7 @@ extern "C" {
 #define SVS_MAX_LAYERS 12
 #define SVS_OPT_MAX_TENSORS 96
 #define SVS_MAX_PEERS 8
-#define SVS_ABI_VERSION 5
+#define SVS_ABI_VERSION 6
 
 typedef enum {
   SVS_OK = 0,
@@ -290,6 +290,17 @@ typedef struct svs_mvs_view {
 int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views,
                      int32_t img_h, int32_t img_w, int32_t inverse_depth, const int32_t* own_view, float* cost_j,
                      float* cost_mvs, uint8_t* valid, void* stream);
+
+/* The same lookup fused with the MVS term of VolSDFLoss (volsdf/model/loss.py:53-67, `get_mvs_loss`): p_i p_j stay in
+ * registers.  weights (N, D) are the rendering weights of the samples; gce the exponent of the generalised cross-entropy
+ * (1: -pw w ; 0: -pw log(w + 1e-8) ; else -pw w.detach()^gce log(w + 1e-8)), confi the confidence threshold on
+ * sum_s p_i p_j.  Outputs: ray_loss (N) = [sum_s p_i p_j > confi] * sum_s term (the loss is its mean over the rays),
+ * conf_ray (N) = sum_s p_i p_j (the sparsity and uncertain-ray terms of the loss branch on it, loss.py:40-45,69-78),
+ * d_weights (N, D) = d ray_loss / d weights (the gradient the compositor backward consumes, before the 1/N and the loss
+ * weight).  D <= 256. */
+int svs_mvs_loss(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views, int32_t img_h,
+                 int32_t img_w, int32_t inverse_depth, const int32_t* own_view, const float* weights, float gce, float confi,
+                 float* ray_loss, float* conf_ray, float* d_weights, void* stream);
 
 #ifdef __cplusplus
 }

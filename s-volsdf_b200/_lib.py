@@ -90,6 +90,7 @@ SIGNATURES = {
     'svs_adam_step_allreduce': (C.c_int, [_I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _I32, _P, _P, _P, _P]),
     'svs_density_backward': (C.c_int, [_P, _I64, _I32, _P, _F, _P, _I32, _P, _P, _P, _P]),
     'svs_cost_mapping': (C.c_int, [_P, _I64, _I32, C.POINTER(MvsView), _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    'svs_mvs_loss': (C.c_int, [_P, _I64, _I32, C.POINTER(MvsView), _I32, _I32, _I32, _I32, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P]),
 }
 
 _lib = None

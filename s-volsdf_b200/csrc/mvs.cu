@@ -60,12 +60,9 @@ __device__ __forceinline__ float trilinear(const float* __restrict__ vol, int Dz
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, float half_w, float half_h, int inverse_depth,
-                    const int32_t* __restrict__ own_view, float* __restrict__ cost_j, float* __restrict__ cost_mvs, uint8_t* __restrict__ valid) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float px = __ldg(xyz + 3 * i), py = __ldg(xyz + 3 * i + 1), pz = __ldg(xyz + 3 * i + 2);
+// the lookup of one sample in all views: p_j (sum over the other views), p_i (the batch's own view), validity
+__device__ __forceinline__ void mvs_lookup(const MvsArgs& a, float px, float py, float pz, float half_w, float half_h, int inverse_depth,
+                                           const int32_t* __restrict__ own_view, float* sum_out, float* own_out, bool* ok_out) {
   float sum = 0.f, own = 0.f;
   bool ok = false;
   const int own_id = own_view ? __ldg(own_view) : 0;
@@ -101,9 +98,80 @@ cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, f
       ok = ok || !bad2;
     }
   }
+  *sum_out = sum;
+  *own_out = ok ? own : 0.f;                                                            // :450
+  *ok_out = ok;
+}
+
+__global__ void __launch_bounds__(256)
+cost_mapping_kernel(const MvsArgs a, const float* __restrict__ xyz, int64_t n, float half_w, float half_h, int inverse_depth,
+                    const int32_t* __restrict__ own_view, float* __restrict__ cost_j, float* __restrict__ cost_mvs, uint8_t* __restrict__ valid) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float sum, own;
+  bool ok;
+  mvs_lookup(a, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), half_w, half_h, inverse_depth, own_view, &sum, &own, &ok);
   cost_j[i] = sum;
-  cost_mvs[i] = ok ? own : 0.f;                                                         // :450
+  cost_mvs[i] = own;
   valid[i] = ok ? 1 : 0;
+}
+
+// Cost lookup fused with the MVS term of VolSDFLoss (volsdf/model/loss.py:53-67): one warp per ray, a lane per sample
+// (D <= 32 * kMvsPerLane).  p_i p_j never leave the registers: the kernel writes the ray's loss term, its confidence
+// sum_s p_i p_j (the sparsity / uncertain-ray terms branch on it) and d(term) / d weights for the compositor backward.
+constexpr int kMvsPerLane = 8;
+__global__ void __launch_bounds__(256)
+mvs_loss_kernel(const MvsArgs a, const float* __restrict__ xyz, const float* __restrict__ weights, int64_t N, int D, float half_w,
+                float half_h, int inverse_depth, const int32_t* __restrict__ own_view, float gce, float confi,
+                float* __restrict__ ray_loss, float* __restrict__ conf_ray, float* __restrict__ d_weights) {
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= N) return;
+  float pw[kMvsPerLane], w[kMvsPerLane];
+  float conf = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMvsPerLane; ++k) {
+    const int s = lane + 32 * k;
+    pw[k] = 0.f;
+    w[k] = 0.f;
+    if (s < D) {
+      const int64_t i = r * D + s;
+      float sum, own;
+      bool ok;
+      mvs_lookup(a, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), half_w, half_h, inverse_depth, own_view, &sum, &own, &ok);
+      pw[k] = own * sum;                  // pi * pj
+      w[k] = __ldg(weights + i);
+      conf += pw[k];
+    }
+  }
+  conf = warp_sum(conf);
+  const float keep = conf > confi ? 1.f : 0.f;   // loss.py:64: only rays the volumes are confident about
+  float term = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMvsPerLane; ++k) {
+    const int s = lane + 32 * k;
+    if (s < D) {
+      float per, dw;
+      if (gce == 1.f) {                   // -pw w
+        per = -pw[k] * w[k];
+        dw = -pw[k];
+      } else if (gce == 0.f) {            // -pw log(w + 1e-8)
+        per = -pw[k] * logf(w[k] + 1e-8f);
+        dw = -pw[k] / (w[k] + 1e-8f);
+      } else {                            // -pw w.detach()^gce log(w + 1e-8)
+        const float wg = powf(w[k], gce);
+        per = -pw[k] * wg * logf(w[k] + 1e-8f);
+        dw = -pw[k] * wg / (w[k] + 1e-8f);
+      }
+      term += per;
+      d_weights[r * D + s] = keep * dw;
+    }
+  }
+  term = warp_sum(term);
+  if (lane == 0) {
+    ray_loss[r] = keep * term;
+    conf_ray[r] = conf;
+  }
 }
 
 }  // namespace svs
@@ -133,6 +201,33 @@ extern "C" int svs_cost_mapping(const float* xyz, int64_t N, int32_t D, const sv
   // (_w - 1) / 2 and (_h - 1) / 2 are Python floats in the reference; the tensor is divided by their fp32 value
   const float half_w = (float)((double)(img_w - 1) / 2.0), half_h = (float)((double)(img_h - 1) / 2.0);
   cost_mapping_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, xyz, n, half_w, half_h, inverse_depth, own_view, cost_j, cost_mvs, valid);
+  SVS_LAUNCH_OK();
+  return SVS_OK;
+}
+
+extern "C" int svs_mvs_loss(const float* xyz, int64_t N, int32_t D, const svs_mvs_view* views, int32_t n_views, int32_t img_h,
+                            int32_t img_w, int32_t inverse_depth, const int32_t* own_view, const float* weights, float gce,
+                            float confi, float* ray_loss, float* conf_ray, float* d_weights, void* stream) {
+  SVS_CHECK_ARG(N >= 0 && D >= 1 && D <= 32 * kMvsPerLane, "svs_mvs_loss: need N >= 0, 1 <= D <= %d (got %d)", 32 * kMvsPerLane, D);
+  SVS_CHECK_ARG(xyz && weights && ray_loss && conf_ray && d_weights && views, "svs_mvs_loss: null pointer");
+  SVS_CHECK_ARG(n_views >= 1 && n_views <= kMaxMvsViews, "svs_mvs_loss: 1 <= n_views <= %d (got %d)", kMaxMvsViews, n_views);
+  SVS_CHECK_ARG(img_h >= 2 && img_w >= 2, "svs_mvs_loss: image resolution must be at least 2 x 2");
+  SVS_CHECK_ARG(gce >= 0.f, "svs_mvs_loss: gce must be >= 0");
+  MvsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_views = n_views;
+  for (int k = 0; k < n_views; ++k) {
+    SVS_CHECK_ARG(views[k].cost && views[k].z_near && views[k].z_far, "svs_mvs_loss: view %d has a null volume", k);
+    SVS_CHECK_ARG(views[k].Dz >= 1 && views[k].H >= 1 && views[k].W >= 1, "svs_mvs_loss: view %d has an empty volume", k);
+    a.v[k] = views[k];
+  }
+  if (N == 0) return SVS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = N * (int64_t)D;
+  ProfScope ps("mvs_loss", 0.0, (double)n * (12.0 + 8.0 + 64.0 * n_views) + 8.0 * (double)N, st);
+  const float half_w = (float)((double)(img_w - 1) / 2.0), half_h = (float)((double)(img_h - 1) / 2.0);
+  mvs_loss_kernel<<<(unsigned)cdiv(N * 32, 256), 256, 0, st>>>(a, xyz, weights, N, D, half_w, half_h, inverse_depth, own_view, gce, confi,
+                                                              ray_loss, conf_ray, d_weights);
   SVS_LAUNCH_OK();
   return SVS_OK;
 }

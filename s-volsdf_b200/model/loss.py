@@ -38,10 +38,17 @@ class VolSDFLoss(nn.Module):
             raise NotImplementedError
 
     # ---- terms ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _conf_ray(model_outputs):
+        """sum_s p_i p_j per ray: from the fused lookup (`CostMapper.mvs_loss`) when it ran, else from pi / pj"""
+        if 'conf_ray' in model_outputs:
+            return model_outputs['conf_ray']
+        return (model_outputs['pi'] * model_outputs['pj']).sum(-1)
+
     def get_rgb_loss(self, rgb_values, rgb_gt, model_outputs=None, t=0):
         rgb_gt = rgb_gt.reshape(-1, 3)
         if t > 0:   # only rays the MVS volumes are uncertain about (loss.py:40-45)
-            uncertain = (model_outputs['pi'] * model_outputs['pj']).sum(-1) < t
+            uncertain = self._conf_ray(model_outputs) < t
             return ((rgb_values - rgb_gt).abs().mean(-1) * uncertain).mean()
         return self.rgb_loss(rgb_values, rgb_gt)
 
@@ -49,6 +56,8 @@ class VolSDFLoss(nn.Module):
         return ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
 
     def get_mvs_loss(self, model_outputs):
+        if 'mvs_loss_fused' in model_outputs:   # lookup + this term in one kernel (svs_mvs_loss), same gce / confi
+            return model_outputs['mvs_loss_fused']
         pw = model_outputs['pi'] * model_outputs['pj']
         w = model_outputs['weights']
         if self.gce == 1:
@@ -61,7 +70,7 @@ class VolSDFLoss(nn.Module):
         return (confident * per_sample.sum(1)).mean()
 
     def get_sparse_loss(self, model_outputs):
-        conf_ray = (model_outputs['pi'] * model_outputs['pj']).sum(-1)
+        conf_ray = self._conf_ray(model_outputs)
         key = 'depth_values_all' if 'depth_values_all' in model_outputs else 'depth_values'
         return ((1. / (model_outputs[key].squeeze() + 1e-3)) * (conf_ray < self.confi)).mean()
 
@@ -73,7 +82,7 @@ class VolSDFLoss(nn.Module):
         counter inside the graph).  Same values as forward() for every iteration."""
         dev = model_outputs['rgb_values'].device
         zero = torch.zeros((), device=dev)
-        has_mvs = 'pi' in model_outputs
+        has_mvs = 'pi' in model_outputs or 'mvs_loss_fused' in model_outputs
         out = {
             'rgb_loss': self.get_rgb_loss(model_outputs['rgb_values'], ground_truth['rgb'].to(dev)),
             'eikonal_loss': self.get_eikonal_loss(model_outputs['grad_theta']) if 'grad_theta' in model_outputs else zero,
@@ -97,7 +106,7 @@ class VolSDFLoss(nn.Module):
         dev = model_outputs['rgb_values'].device
         zero = torch.zeros((), device=dev)
         rgb_gt = ground_truth['rgb'].to(dev)
-        has_mvs = 'pi' in model_outputs
+        has_mvs = 'pi' in model_outputs or 'mvs_loss_fused' in model_outputs
         annealing = self.sparse_weight > 0 and self.anneal_rgb > 0 and self.iter_step < self.anneal_rgb
         out = {
             'rgb_loss': self.get_rgb_loss(model_outputs['rgb_values'], rgb_gt),

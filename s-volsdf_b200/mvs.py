@@ -44,12 +44,7 @@ class CostMapper(object):
     def __call__(self, z_vals, ts, xyz_raw):
         return self.cost_mapping(z_vals, ts, xyz_raw)
 
-    @torch.no_grad()
-    def cost_mapping(self, z_vals, ts, xyz_raw):
-        """z_vals (N, D) is only the shape / device template the reference uses it as; ts: batch image index
-        (`ts[0] == id_k` marks the batch's own view, vsdf.py:392); xyz_raw (N, D, 3) world points."""
-        xyz = xyz_raw.detach().float().contiguous()
-        N, D = int(xyz.shape[0]), int(xyz.shape[1])
+    def _views(self, ts):
         # a CUDA int32 tensor keeps the choice of the own view on the device (CUDA-graph replays with changing batches,
         # svolsdf_b200.train.GraphedTrainStep); anything else is read on the host like the reference's `ts[0] == id_k`
         own_dev = ts if (torch.is_tensor(ts) and ts.is_cuda and ts.dtype == torch.int32) else None
@@ -59,6 +54,23 @@ class CostMapper(object):
             arr[i] = v
             arr[i].view_id = self.view_ids[i]
             arr[i].same_view = 1 if self.view_ids[i] == own else 0
+        return arr, own_dev
+
+    def mvs_loss(self, weights, ts, xyz_raw, gce=1, confi=0):
+        """Cost lookup FUSED with the MVS term of the loss (`VolSDFLoss.get_mvs_loss`, volsdf/model/loss.py:53-67): one
+        kernel (`svs_mvs_loss`) reads the volumes, forms p_i p_j in registers and returns
+          mvs_loss  () = mean over rays of [sum_s p_i p_j > confi] * sum_s term(p_i p_j, weights)   (differentiable in `weights`)
+          conf_ray (N,) = sum_s p_i p_j   (no gradient; the loss's sparsity / uncertain-ray terms branch on it)
+        — p_i, p_j never reach HBM and the backward is a multiply of the stored d term / d weights."""
+        return _MvsLossFn.apply(self, weights, ts, xyz_raw, float(gce), float(confi))
+
+    @torch.no_grad()
+    def cost_mapping(self, z_vals, ts, xyz_raw):
+        """z_vals (N, D) is only the shape / device template the reference uses it as; ts: batch image index
+        (`ts[0] == id_k` marks the batch's own view, vsdf.py:392); xyz_raw (N, D, 3) world points."""
+        xyz = xyz_raw.detach().float().contiguous()
+        N, D = int(xyz.shape[0]), int(xyz.shape[1])
+        arr, own_dev = self._views(ts)
         dev = xyz.device
         cost_j = torch.empty(N, D, dtype=torch.float32, device=dev)
         cost_mvs = torch.empty(N, D, dtype=torch.float32, device=dev)
@@ -66,3 +78,30 @@ class CostMapper(object):
         L.call('svs_cost_mapping', L.ptr(xyz), N, D, arr, len(self._desc), self.img_res[0], self.img_res[1],
                1 if self.inverse_depth else 0, L.ptr(own_dev), L.ptr(cost_j), L.ptr(cost_mvs), L.ptr(valid), L.stream())
         return cost_j, cost_mvs, valid.bool()
+
+
+class _MvsLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mapper, weights, ts, xyz_raw, gce, confi):
+        xyz = xyz_raw.detach().float().contiguous()
+        w = weights.detach().float().contiguous()
+        N, D = int(xyz.shape[0]), int(xyz.shape[1])
+        if tuple(w.shape) != (N, D):
+            raise L.SvsError('mvs_loss: weights %s do not match the samples (%d, %d)' % (tuple(w.shape), N, D))
+        arr, own_dev = mapper._views(ts)
+        dev = xyz.device
+        ray_loss = torch.empty(N, dtype=torch.float32, device=dev)
+        conf_ray = torch.empty(N, dtype=torch.float32, device=dev)
+        d_w = torch.empty(N, D, dtype=torch.float32, device=dev)
+        L.call('svs_mvs_loss', L.ptr(xyz), N, D, arr, len(mapper._desc), mapper.img_res[0], mapper.img_res[1],
+               1 if mapper.inverse_depth else 0, L.ptr(own_dev), L.ptr(w), gce, confi, L.ptr(ray_loss), L.ptr(conf_ray),
+               L.ptr(d_w), L.stream())
+        ctx.save_for_backward(d_w)
+        ctx.n_rays = max(N, 1)
+        ctx.mark_non_differentiable(conf_ray)
+        return ray_loss.mean(), conf_ray
+
+    @staticmethod
+    def backward(ctx, g_loss, g_conf):
+        (d_w,) = ctx.saved_tensors
+        return None, d_w * (g_loss / ctx.n_rays), None, None, None, None

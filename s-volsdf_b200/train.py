@@ -39,11 +39,12 @@ class GraphedTrainStep(object):
     Optimizers other than FusedAdam get no NaN guard inside the graph (on_after_backward needs a host sync)."""
 
     def __init__(self, model, optimizer, loss_fn=default_loss, example_input=None, example_gt=None, grad_clip=1.0,
-                 reducer=None, world=1, make_rng=None, warmup=3, cost_mapper=None, own_view=0, iter_step=0):
+                 reducer=None, world=1, make_rng=None, warmup=3, cost_mapper=None, own_view=0, iter_step=0, fused_mvs=True):
         assert example_input is not None and example_gt is not None
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
         self.grad_clip, self.reducer, self.world = grad_clip, reducer, world
         self.cost_mapper = cost_mapper
+        self.fused_mvs = bool(fused_mvs)
         self.module_loss = hasattr(loss_fn, 'forward_device')
         if getattr(loss_fn, 'iter_step', None) is not None and not self.module_loss:
             raise ValueError('loss modules with a host-side step counter cannot be captured (their annealing would freeze); '
@@ -101,7 +102,12 @@ class GraphedTrainStep(object):
         self.rng.rewind()
         out = self.model(self.inp, fast=1)
         if self.cost_mapper is not None:   # vsdf.py:207-209
-            out['pj'], out['pi'], _ = self.cost_mapper(out['depth_vals'], self.own_view, out['xyz'])
+            if self.module_loss and getattr(self.loss_fn, 'mvs_weight', 0) > 0 and self.fused_mvs:
+                # lookup + GCE term in one kernel: p_i p_j stay in registers
+                out['mvs_loss_fused'], out['conf_ray'] = self.cost_mapper.mvs_loss(
+                    out['weights'], self.own_view, out['xyz'], gce=self.loss_fn.gce, confi=self.loss_fn.confi)
+            else:
+                out['pj'], out['pi'], _ = self.cost_mapper(out['depth_vals'], self.own_view, out['xyz'])
         if self.module_loss:
             loss = self.loss_fn.forward_device(out, self.gt, self.iter_step)['loss']
             self.iter_step.add_(1.0)

@@ -31,7 +31,7 @@ def test_ctypes_table_matches_header():
 
 def test_abi_version_and_engine_query():
     lib = L.load()
-    assert lib.svs_abi_version() == 5
+    assert lib.svs_abi_version() == 6
     assert lib.svs_has_engine(L.ENGINE_FP32) == 1
 
 
@@ -80,6 +80,12 @@ def test_argument_validation_and_empty_inputs_need_no_gpu():
     assert b'n_views' in lib.svs_last_error()
     assert lib.svs_cost_mapping(p, 4, 20, v, 0, 72, 96, 1, None, p, p, p, None) < 0
     assert lib.svs_cost_mapping(p, 4, 20, v, 3, 1, 96, 1, None, p, p, p, None) < 0            # degenerate image
+    # ... fused with the loss's MVS term
+    f = C.c_float
+    assert lib.svs_mvs_loss(p, 0, 20, v, 3, 72, 96, 1, None, p, f(0.5), f(0.0), p, p, p, None) == 0     # no rays
+    assert lib.svs_mvs_loss(p, 4, 300, v, 3, 72, 96, 1, None, p, f(0.5), f(0.0), p, p, p, None) < 0    # D > 256
+    assert lib.svs_mvs_loss(p, 4, 20, v, 3, 72, 96, 1, None, None, f(0.5), f(0.0), p, p, p, None) < 0  # no weights
+    assert lib.svs_mvs_loss(p, 4, 20, v, 3, 72, 96, 1, None, p, f(-1.0), f(0.0), p, p, p, None) < 0    # negative exponent
     v[1].cost = None
     assert lib.svs_cost_mapping(p, 4, 20, v, 3, 72, 96, 1, None, p, p, p, None) < 0
     assert b'view 1' in lib.svs_last_error()

@@ -378,3 +378,46 @@ def test_cost_mapping_own_view_on_the_device():
         b = cm(z, torch.tensor([own], dtype=torch.int32, device=DEV), xyz)
         for x, y in zip(a, b):
             assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('gce,confi', [(1, 0.0), (0, 0.0), (0.5, 0.0), (0.5, 0.02)])
+def test_fused_mvs_loss_matches_lookup_plus_loss_module(gce, confi):
+    """`CostMapper.mvs_loss` (svs_mvs_loss: lookup + GCE term + d/d weights in one kernel, p_i p_j in registers) against
+    the two-step path — `CostMapper.cost_mapping` (checked against the reference's golden above) followed by
+    `VolSDFLoss.get_mvs_loss` (pinned to the reference's loss in test_oracle_vs_golden.py) with torch autograd."""
+    from svolsdf_b200.model.loss import VolSDFLoss
+    views = S.mvs_views(n_views=3, dz=48, h=72, w=96, img_res=(288, 384), seed=9)
+    n_rays, n_samples = 777, 98
+    xyz = S.mvs_points(n_rays, n_samples, seed=12).to(DEV)
+    ids, cm = _mapper(views, (288, 384), True)
+    g = torch.Generator().manual_seed(3)
+    w = torch.softmax(torch.randn(n_rays, n_samples, generator=g) * 2, dim=1).to(DEV).requires_grad_(True)
+    own = torch.tensor([ids[1]])
+    # two-step reference path
+    pj, pi, _ = cm(torch.zeros(n_rays, n_samples, device=DEV), own, xyz)
+    loss_mod = VolSDFLoss(rgb_loss='torch.nn.L1Loss', eikonal_weight=0.1, mvs_weight=1.0, gce=gce, confi=confi)
+    ref = loss_mod.get_mvs_loss({'pi': pi, 'pj': pj, 'weights': w})
+    (g_ref,) = torch.autograd.grad(ref, w)
+    conf_ref = (pi * pj).sum(-1)
+    # fused
+    w2 = w.detach().clone().requires_grad_(True)
+    val, conf = cm.mvs_loss(w2, own, xyz, gce=gce, confi=confi)
+    (g_fused,) = torch.autograd.grad(val * 3.0, w2)          # upstream factor: the backward scales the stored gradient
+    assert not conf.requires_grad
+    assert rel_err(conf.cpu(), conf_ref.cpu()) < 1e-6
+    assert abs(float(val) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert rel_err(g_fused.cpu() / 3.0, g_ref.cpu()) < 1e-5
+    assert float((conf_ref > confi).float().mean()) > 0.05   # the confidence test keeps some rays and drops others
+    # the loss module takes the fused value and the ray confidences in place of pi / pj
+    out = {'mvs_loss_fused': val, 'conf_ray': conf, 'weights': w2}
+    assert loss_mod.get_mvs_loss(out) is val
+    assert torch.equal(loss_mod._conf_ray(out), conf)
+
+
+def test_fused_mvs_loss_rejects_bad_arguments():
+    views = S.mvs_views(n_views=1, dz=4, h=6, w=8, img_res=(12, 16))
+    ids, cm = _mapper(views, (12, 16), True)
+    with pytest.raises(L.SvsError):   # weights do not match the samples
+        cm.mvs_loss(torch.zeros(2, 3, device=DEV), torch.tensor([0]), torch.zeros(2, 2, 3, device=DEV))
+    with pytest.raises(L.SvsError):   # more samples per ray than a warp covers
+        cm.mvs_loss(torch.zeros(2, 300, device=DEV), torch.tensor([0]), torch.zeros(2, 300, 3, device=DEV))
