@@ -235,3 +235,23 @@ torch.save(out, sys.argv[1])
     for k in res['0']:
         if k.startswith('g_'):
             assert rel_err(res['1'][k], res['0'][k]) < 1e-4, (k, rel_err(res['1'][k], res['0'][k]))
+
+
+def test_mesh_grid_and_point_queries_vs_fp64_oracle():
+    """svolsdf_b200.mesh.sdf_grid / sdf_points (the reference's meshing queries `model.implicit_network(x)[:, 0]`,
+    utils/plots.py:61,69-76) on the benchmarked engine against the fp64 oracle — ragged chunks, an odd
+    number of tiles per chunk, points outside the bounding sphere (raw network output: no clamp in this query)."""
+    from svolsdf_b200.mesh import sdf_grid, sdf_points
+    m = build_model('dtu', perturb=True, device=DEV).eval().set_engine(L.ENGINE_TC_SPLIT)
+    sd = {k: v.double() for k, v in state_dict_cpu(m).items()}
+    grid, axes = sdf_grid(m, resolution=33, bound=(-1.2, 1.2, -0.9, 1.5, -3.5, 3.5), chunk=7001)
+    assert grid.shape == (33, 33, 33)
+    pts = torch.stack(torch.meshgrid(*[a.cpu() for a in axes], indexing='ij'), -1).reshape(-1, 3)
+    with torch.no_grad():
+        ref = O.sdf_net(sd, 'implicit_network', pts.double(), 6)[:, 0]
+    assert max_abs(grid.reshape(-1).cpu(), ref) < 5e-5, max_abs(grid.reshape(-1).cpu(), ref)
+    assert float(grid.min()) < 0 < float(grid.max())       # the surface crosses the box
+    x = _points(5003, seed=4)
+    with torch.no_grad():
+        ref_p = O.sdf_net(sd, 'implicit_network', x.double(), 6)[:, 0]
+    assert max_abs(sdf_points(m, x.to(DEV), chunk=999).cpu(), ref_p) < 5e-5
