@@ -35,7 +35,7 @@ def _points(n, scale=2.4, seed=5, d=3):
 
 def test_library_loaded_is_ours():
     import svolsdf_b200._lib as L
-    assert L.load().svs_abi_version() == 5
+    assert L.load().svs_abi_version() == 6
     assert L.LIB_PATH.endswith('libsvolsdf_b200.so')
 
 
