@@ -1,4 +1,4 @@
-// sm_100a building blocks written as inline PTX: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma /
+// sm_100a building blocks written as inline PTX: mbarrier, 1-D bulk copies (cp.async.bulk), tcgen05 (alloc / mma /
 // commit / ld / fences), UMMA shared-memory and instruction descriptors.
 //
 // Bit layouts follow the PTX ISA "tcgen05" chapter; the field positions were cross-checked against the
@@ -65,20 +65,6 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   while (!mbar_try(bar, parity)) __nanosleep(40);
 }
 
-// ---------------------------------------------------------------- TMA
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
-}
-// 2-D tile load: coordinates (c0 = innermost element index, c1 = row index); completes `bytes` on `bar`
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-
 // ---------------------------------------------------------------- proxies / bulk copies (1-D TMA, SASS: UBLKCP)
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -94,10 +80,6 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"((uint64_t)dst), "r"(smem_u32(src)),
                "r"(bytes)
                : "memory");
-}
-// global -> L2 only (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((uint64_t)src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
