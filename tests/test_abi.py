@@ -90,3 +90,25 @@ def test_argument_validation_and_empty_inputs_need_no_gpu():
     assert lib.svs_cost_mapping(p, 4, 20, v, 3, 72, 96, 1, None, p, p, p, None) < 0
     assert b'view 1' in lib.svs_last_error()
     assert lib.svs_cost_mapping(None, 4, 20, v, 3, 72, 96, 1, None, p, p, p, None) < 0
+
+
+def test_dy_staging_index_arithmetic_is_exact():
+    """The backward chain converts a tile's fp32 dy rows from a flat staging buffer: row of flat element e = umulhi(e,
+    ceil(2^32 / ldy)) (csrc/mlp_tc_chains.cuh: dy_magic; csrc/mlp_tc.cuh: PRO_DY).  Exact for every element of a 128-row
+    tile at every row length the path accepts (128 * ldy < 65536), and the 16-byte bulk / direct-load split of a partial
+    last tile covers every valid float exactly once."""
+    import numpy as np
+    for ldy in list(range(1, 64)) + [257, 258, 300, 320, 511]:
+        if 128 * ldy >= 65536:
+            continue
+        magic = (1 << 32) // ldy + 1
+        e = np.arange(128 * ldy, dtype=np.uint64)
+        row = (e * np.uint64(magic)) >> np.uint64(32)
+        assert np.array_equal(row, e // np.uint64(ldy)), ldy
+    ldy = 257
+    for rows in (1, 2, 3, 57, 127, 128):
+        total = (rows * ldy * 4) & ~15           # bytes moved by bulk copies
+        n_el = rows * ldy
+        from_smem = sum(1 for e in range(n_el) if e * 4 + 4 <= total)
+        direct = sum(1 for e in range(n_el) if not (e * 4 + 4 <= total))
+        assert from_smem == total // 4 and from_smem + direct == n_el and direct <= 3
