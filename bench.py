@@ -37,7 +37,8 @@ def parse():
     ap.add_argument('--rays', type=int, default=1024, help='rays per GPU per step')
     ap.add_argument('--engine', default='auto', choices=['auto', 'fp32', 'tc', 'tc_split'],
                     help='auto = tc_split: the tcgen05 engine that meets the parity contract')
-    ap.add_argument('--cpu-rays', type=int, default=128, help='rays per step of the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-rays', type=int, default=1024, help='rays per step of the bounded CPU-baseline sample (default: the headline config)')
+    ap.add_argument('--cpu-steps', type=int, default=6, help='timed steps of the CPU-baseline sample (1 warm-up before them; ~1.8 s each at 1024 rays)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='all', choices=['all', 'train', 'frame'],
                     help="all (default): the headline train step (BASELINE configs[1]) plus `frame` (configs[2]) and `large_batch` "
@@ -720,7 +721,7 @@ def run_ours(args):
             mvs = {'error': str(e).splitlines()[0][:200]}
     if world == 1:
         if not args.no_cpu_baseline:
-            cpu = cpu_train_steps(args.cpu_rays, 2, 1)
+            cpu = cpu_train_steps(args.cpu_rays, max(1, args.cpu_steps), 1)     # ~10-15 s of CPU work
             cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
         if 'parity' not in skip and not bmvs:
             try:
