@@ -302,3 +302,20 @@ def test_loss_forward_device_equals_forward_on_every_side_of_the_annealing_switc
             rb = b.forward_device(out, gt, torch.tensor(float(it)))
             for k in ra:
                 assert abs(float(ra[k]) - float(rb[k])) < 1e-6, (kw, it, k)
+
+
+def test_survey_sanity_anchors_at_1024_rays():
+    """numbers the survey session measured on the unmodified reference (DTU scene of 8d, 1024 rays, CPU, model
+    seed 0, uv seed 1, eval forward) — an anchor at the BENCHMARKED size that is independent of oracle/make_golden.py."""
+    from helpers import build_model
+    model = build_model('dtu')
+    assert sum(p.numel() for p in model.parameters()) == 797883
+    assert abs(float(sum(p.detach().double().sum() for p in model.parameters())) - 10576.36656) < 1e-4
+    torch.manual_seed(123)
+    rng = O.draw_rng(1024, False, bg=False, n_final=98)      # eval draws nothing random (uniform extras are deterministic)
+    out = O.volsdf_forward(state_dict_cpu(model), conf_of('dtu'), S.make_input('dtu', 1024), False, fast=-1, rng=rng)
+    assert len(out['trace'].iters) == 2                      # beta = 0.1 converges in two sampler iterations (SURVEY 8d)
+    assert abs(float(out['rgb_values'].mean()) - 0.4996191) < 2e-6
+    assert abs(float(out['depth_values'].mean()) - 2.2140082) < 5e-6
+    assert abs(float(out['normal_map'].mean()) - (-0.3475780)) < 2e-6
+    assert float((out['weights'].sum(1) - 1.0).abs().max()) < 1e-5
